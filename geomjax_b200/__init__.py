@@ -1,0 +1,14 @@
+"""geomjax_b200: B200-native batched-chain engine for geomjax's Riemannian samplers.
+
+Drop-in for the reference's hot path only (geomjax/__init__.py:17-25 names):
+``rmhmc``, ``lmc``, ``lmcmonge`` (+ ``rhat``, ``ess``, ``step_size_adaptation``,
+``window_adaptation``, ``dual_averaging``), operating on a leading chain axis and executing as
+hand-written CUDA for sm_100a behind the C ABI of ``include/geomb200.h``.
+"""
+from . import integrators, random, targets  # noqa: F401
+from .base import AdaptationAlgorithm, AdaptationResults, SamplingAlgorithm  # noqa: F401
+from .samplers import (LMCInfo, LMCState, Proposal, RMHMCInfo, RMHMCState, lmc, lmcmonge, rmhmc,  # noqa: F401
+                       run_fused)
+from .targets import TargetDescriptor, neal_funnel  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,254 @@
+// C-ABI entry points (include/geomb200.h).  No torch types; plain pointers and sizes.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include "launch.h"
+
+namespace gb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------- PRNG test-surface kernels
+__global__ void k_split(const uint32_t* keys, uint32_t* out, long long n, int num, int mode) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * num) return;
+  long long kk = i / num;
+  U2 r = split_index(mode, U2{keys[2 * kk], keys[2 * kk + 1]}, (uint32_t)num, (uint32_t)(i % num));
+  out[2 * i] = r.x;
+  out[2 * i + 1] = r.y;
+}
+template <int WHAT>
+__global__ void k_draw(const uint32_t* keys, void* out, long long n, int count, int mode) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * count) return;
+  long long kk = i / count;
+  uint32_t b = random_bits_elem(mode, U2{keys[2 * kk], keys[2 * kk + 1]}, (uint32_t)(i % count), (uint32_t)count);
+  if (WHAT == 0) ((uint32_t*)out)[i] = b;
+  if (WHAT == 1) ((float*)out)[i] = bits_to_unit_float(b);
+  if (WHAT == 2) ((float*)out)[i] = bits_to_normal(b);
+}
+__global__ void k_chain_keys(U2 root, long long t, long long T, long long off, long long Ctot, uint32_t* out,
+                             long long C, int mode) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  U2 r = chain_key(mode, root, (uint32_t)T, (uint32_t)t, (uint32_t)Ctot, (uint32_t)(off + i));
+  out[2 * i] = r.x;
+  out[2 * i + 1] = r.y;
+}
+
+// ---------------------------------------------------------------- dual averaging
+template <typename R>
+__global__ void k_da_init(R* da, const R* eps0, long long C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  const R x = eps0[i];
+  da[5 * i + 0] = log(x);
+  da[5 * i + 1] = R(0);
+  da[5 * i + 2] = R(1);
+  da[5 * i + 3] = R(0);
+  da[5 * i + 4] = log(R(10) * x);
+}
+template <typename R>
+__global__ void k_da_update(R* da, const R* acc, R target, R t0, R gamma, R kappa, long long C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  dual_averaging_update<R>(da + 5 * i, acc[i], target, t0, gamma, kappa);
+}
+
+// ---------------------------------------------------------------- FP32 peak microbenchmark
+__global__ void k_fp32_peak(float* out, long long iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999f, c = 1e-4f;
+  for (long long i = 0; i < iters; i += 8) {
+    a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+    a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+  }
+  float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456f) out[0] = s;  // never true in practice; keeps the loop alive
+}
+
+static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" {
+
+int gb200_version(void) { return GB200_VERSION; }
+const char* gb200_last_error(void) { return g_err; }
+
+int gb200_threefry_split(const uint32_t* keys, uint32_t* out, int64_t n, int32_t num, int32_t mode, void* stream) {
+  if (!keys || !out || n < 0 || num <= 0) { set_error("threefry_split: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (n == 0) return GB200_OK;
+  k_split<<<nblk(n * num, 256), 256, 0, (cudaStream_t)stream>>>(keys, out, n, num, mode);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+#define GB_DRAW(NAME, WHAT, T)                                                                                      \
+  int NAME(const uint32_t* keys, T* out, int64_t n, int32_t count, int32_t mode, void* stream) {                    \
+    if (!keys || !out || n < 0 || count <= 0) { set_error(#NAME ": bad argument"); return GB200_ERR_INVALID_ARGUMENT; } \
+    if (n == 0) return GB200_OK;                                                                                    \
+    k_draw<WHAT><<<nblk(n * count, 256), 256, 0, (cudaStream_t)stream>>>(keys, out, n, count, mode);                \
+    GB_CHECK_LAUNCH();                                                                                              \
+    return GB200_OK;                                                                                                \
+  }
+GB_DRAW(gb200_random_bits, 0, uint32_t)
+GB_DRAW(gb200_uniform_f32, 1, float)
+GB_DRAW(gb200_normal_f32, 2, float)
+
+int gb200_chain_keys(const uint32_t root_key[2], int64_t t, int64_t total_transitions, int64_t chain_offset,
+                     int64_t total_chains, uint32_t* out, int64_t C, int32_t mode, void* stream) {
+  if (!root_key || !out || C < 0 || t < 0 || t >= total_transitions || chain_offset + C > total_chains) {
+    set_error("chain_keys: bad argument");
+    return GB200_ERR_INVALID_ARGUMENT;
+  }
+  if (C == 0) return GB200_OK;
+  k_chain_keys<<<nblk(C, 256), 256, 0, (cudaStream_t)stream>>>(U2{root_key[0], root_key[1]}, t, total_transitions,
+                                                             chain_offset, total_chains, out, C, mode);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+
+static int check_target(const gb200_target_desc* t) {
+  if (!t) { set_error("target descriptor is NULL"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (t->D < 1) { set_error("target: D must be >= 1"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (t->kind == GB200_TARGET_FUNNEL && t->D < 2) { set_error("funnel: D must be >= 2"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (t->kind == GB200_TARGET_BANANA && t->D != 2) { set_error("banana: D must be 2"); return GB200_ERR_INVALID_ARGUMENT; }
+  return GB200_OK;
+}
+
+int gb200_init(const gb200_target_desc* target, gb200_state st, int64_t C, int32_t dtype, void* stream) {
+  int rc = check_target(target);
+  if (rc) return rc;
+  if (C == 0) return GB200_OK;
+  if (!st.position || !st.logdensity || !st.logdensity_grad || C < 0) { set_error("init: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
+  LayoutChoice lay;
+  if (!choose_layout(target->D, 0, C, &lay)) { set_error("init: D=%d too large", target->D); return GB200_ERR_UNSUPPORTED; }
+  return launch_init(*target, st, C, lay, dtype, (cudaStream_t)stream);
+}
+
+int gb200_step(int32_t sampler, const gb200_kernel_params* p, const gb200_target_desc* target,
+               const gb200_key_source* keys, gb200_state in, gb200_state out, const gb200_info* info,
+               const gb200_run_opts* opts, int64_t C, void* stream) {
+  int rc = check_target(target);
+  if (rc) return rc;
+  if (!p || !keys) { set_error("step: params/keys NULL"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (C < 0 || p->num_integration_steps < 0) { set_error("step: negative size"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (C == 0) return GB200_OK;
+  if (!in.position || !in.logdensity || !in.logdensity_grad || !out.position || !out.logdensity || !out.logdensity_grad) {
+    set_error("step: state pointer NULL");
+    return GB200_ERR_INVALID_ARGUMENT;
+  }
+  if (sampler != GB200_RMHMC && (!in.volume_adjustment || !out.volume_adjustment)) {
+    set_error("step: LMC kernels need volume_adjustment");
+    return GB200_ERR_INVALID_ARGUMENT;
+  }
+  if (keys->keys == nullptr) {
+    if (keys->num_transitions < 1 || keys->first_transition < 0 ||
+        keys->first_transition + keys->num_transitions > keys->total_transitions ||
+        keys->chain_offset < 0 || keys->chain_offset + C > keys->total_chains) {
+      set_error("step: inconsistent key source (t0=%lld T=%lld of %lld, chains %lld+%lld of %lld)",
+                (long long)keys->first_transition, (long long)keys->num_transitions, (long long)keys->total_transitions,
+                (long long)keys->chain_offset, (long long)C, (long long)keys->total_chains);
+      return GB200_ERR_INVALID_ARGUMENT;
+    }
+    if (keys->total_transitions > 0x7fffffffLL || keys->total_chains > 0x7fffffffLL) {
+      set_error("step: split widths beyond 2^31 are not supported");
+      return GB200_ERR_UNSUPPORTED;
+    }
+  }
+  const long long T = keys->keys ? 1 : keys->num_transitions;
+  if (opts && T > 1 && (opts->noise_override || opts->uniform_override)) {
+    set_error("step: noise/uniform overrides require num_transitions == 1");
+    return GB200_ERR_INVALID_ARGUMENT;
+  }
+  if (p->threefry_mode != GB200_THREEFRY_LEGACY && p->threefry_mode != GB200_THREEFRY_PARTITIONABLE) {
+    set_error("step: unknown threefry mode %d", p->threefry_mode);
+    return GB200_ERR_INVALID_ARGUMENT;
+  }
+  if (C == 0) return GB200_OK;
+
+  TransArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in_pos = in.position; a.in_logp = in.logdensity; a.in_grad = in.logdensity_grad; a.in_vol = in.volume_adjustment;
+  a.out_pos = out.position; a.out_logp = out.logdensity; a.out_grad = out.logdensity_grad; a.out_vol = out.volume_adjustment;
+  if (info) a.info = *info;
+  if (opts) a.opts = *opts;
+  a.ks = *keys;
+  a.step_size = p->step_size;
+  a.step_size_per_chain = p->step_size_per_chain;
+  a.inv_mass = p->inverse_mass_matrix;
+  a.alpha2 = p->alpha2;
+  a.divergence_threshold = p->divergence_threshold;
+  a.fp_tol = p->fp_convergence_tol;
+  a.fp_div_tol = p->fp_divergence_tol;
+  a.fp_max_iters = p->fp_max_iters;
+  a.num_steps = p->num_integration_steps;
+  a.half_step = p->half_step;
+  a.D = target->D;
+  a.metric = target->metric;
+  a.mode = p->threefry_mode;
+  a.C = C;
+
+  LayoutChoice lay;
+  if (!choose_layout(target->D, p->lanes_per_chain, C, &lay)) {
+    set_error("step: no layout for D=%d lanes_per_chain=%d", target->D, p->lanes_per_chain);
+    return GB200_ERR_UNSUPPORTED;
+  }
+  switch (sampler) {
+    case GB200_LMCMONGE: return launch_lmcmonge(a, *target, lay, p->dtype, (cudaStream_t)stream);
+    case GB200_LMC: return launch_lmc(a, *target, lay, p->dtype, (cudaStream_t)stream);
+    case GB200_RMHMC: return launch_rmhmc(a, *target, lay, p->dtype, (cudaStream_t)stream);
+    default: set_error("step: unknown sampler %d", sampler); return GB200_ERR_INVALID_ARGUMENT;
+  }
+}
+
+int gb200_rmhmc_step(const gb200_kernel_params* p, const gb200_target_desc* t, const gb200_key_source* k, gb200_state in,
+                     gb200_state out, const gb200_info* info, const gb200_run_opts* o, int64_t C, void* s) {
+  return gb200_step(GB200_RMHMC, p, t, k, in, out, info, o, C, s);
+}
+int gb200_lmc_step(const gb200_kernel_params* p, const gb200_target_desc* t, const gb200_key_source* k, gb200_state in,
+                   gb200_state out, const gb200_info* info, const gb200_run_opts* o, int64_t C, void* s) {
+  return gb200_step(GB200_LMC, p, t, k, in, out, info, o, C, s);
+}
+int gb200_lmcmonge_step(const gb200_kernel_params* p, const gb200_target_desc* t, const gb200_key_source* k, gb200_state in,
+                        gb200_state out, const gb200_info* info, const gb200_run_opts* o, int64_t C, void* s) {
+  return gb200_step(GB200_LMCMONGE, p, t, k, in, out, info, o, C, s);
+}
+
+int gb200_dual_averaging_init(void* da, const void* eps0, int64_t C, int32_t dtype, void* stream) {
+  if (!da || !eps0 || C < 0) { set_error("dual_averaging_init: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (dtype != GB200_F32) { set_error("dual_averaging: float32 only"); return GB200_ERR_UNSUPPORTED; }
+  if (C == 0) return GB200_OK;
+  k_da_init<float><<<nblk(C, 256), 256, 0, (cudaStream_t)stream>>>((float*)da, (const float*)eps0, C);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+int gb200_dual_averaging_update(void* da, const void* acc, double target, double t0, double gamma, double kappa,
+                                int64_t C, int32_t dtype, void* stream) {
+  if (!da || !acc || C < 0) { set_error("dual_averaging_update: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (dtype != GB200_F32) { set_error("dual_averaging: float32 only"); return GB200_ERR_UNSUPPORTED; }
+  if (C == 0) return GB200_OK;
+  k_da_update<float><<<nblk(C, 256), 256, 0, (cudaStream_t)stream>>>((float*)da, (const float*)acc, (float)target,
+                                                                     (float)t0, (float)gamma, (float)kappa, C);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+
+int gb200_fp32_peak_kernel(float* out, int32_t grid, int32_t block, int64_t iters, void* stream) {
+  if (!out || grid < 1 || block < 1 || block > 1024) { set_error("fp32_peak: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
+  k_fp32_peak<<<grid, block, 0, (cudaStream_t)stream>>>(out, iters);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+// R-hat and ESS as shard-local sufficient statistics + host finalisation.
+// Reference: geomjax/diagnostics.py:25-75 (potential_scale_reduction), :78-209
+// (effective_sample_size).  samples[T, C, D] with sample_axis=0, chain_axis=1
+// (examples/funnel/main.py:77-78).  Every partial is a plain SUM over chains so that shards on
+// different GPUs combine with one all-reduce(sum).
+#include <math.h>
+#include <stdlib.h>
+#include <vector>
+#include "launch.h"
+
+namespace gb {
+
+// ---- R-hat partial: per (chain, dim) mean and ddof=1 variance over samples, summed over chains.
+// stats layout: [0,D) sum_c mean; [D,2D) sum_c mean^2; [2D,3D) sum_c var; [3D] chains counted.
+template <typename R>
+__global__ void k_rhat_partial(const R* __restrict__ x, long long T, long long C, int D, double* stats) {
+  extern __shared__ double sh[];  // 3*D
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) sh[i] = 0.0;
+  __syncthreads();
+  const long long CD = C * D;
+  // stride is a multiple of D when gridDim*blockDim is; enforce by rounding the stride
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long stride = (nthreads / D) * D;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (stride > 0 && tid < stride) {
+    const int d = (int)(tid % D);
+    double sm = 0.0, sm2 = 0.0, sv = 0.0;
+    for (long long i = tid; i < CD; i += stride) {
+      double s1 = 0.0, s2 = 0.0;
+      const double x0 = (double)x[i];
+      for (long long t = 0; t < T; ++t) {
+        const double v = (double)x[t * CD + i] - x0;  // shifted sums: no cancellation
+        s1 += v;
+        s2 += v * v;
+      }
+      const double mean_sh = s1 / (double)T;
+      const double var = (s2 - (double)T * mean_sh * mean_sh) / (double)(T - 1);
+      const double mean = mean_sh + x0;
+      sm += mean;
+      sm2 += mean * mean;
+      sv += var;
+    }
+    atomicAdd(&sh[d], sm);
+    atomicAdd(&sh[D + d], sm2);
+    atomicAdd(&sh[2 * D + d], sv);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) atomicAdd(&stats[i], sh[i]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[3 * D], (double)C);
+}
+
+// ---- ESS partial: chain-summed biased autocovariance for lag < num_lags.
+// One block = one dimension d and S chains whose centred series sit in shared memory; thread l
+// accumulates lag l over all S series and issues one atomic per (block, lag).
+template <typename R>
+__global__ void k_ess_partial(const R* __restrict__ x, long long T, long long C, int D, int num_lags, int S,
+                              double* acov) {
+  extern __shared__ float xs[];  // S * T
+  const int d = blockIdx.y;
+  const long long c0 = (long long)blockIdx.x * S;
+  const int ns = (int)min((long long)S, C - c0);
+  const long long CD = C * D;
+  for (long long i = threadIdx.x; i < (long long)ns * T; i += blockDim.x) {
+    const int s = (int)(i % ns);
+    const long long t = i / ns;
+    xs[(long long)s * T + t] = (float)x[t * CD + (c0 + s) * D + d];
+  }
+  __syncthreads();
+  // centre each series on its own mean (diagnostics.py:122-124)
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarp = blockDim.x / 32;
+  for (int s = warp; s < ns; s += nwarp) {
+    double sum = 0.0;
+    for (long long t = lane; t < T; t += 32) sum += (double)xs[(long long)s * T + t];
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float m = (float)(sum / (double)T);
+    for (long long t = lane; t < T; t += 32) xs[(long long)s * T + t] -= m;
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < num_lags; l += blockDim.x) {
+    double tot = 0.0;
+    if (l < T) {
+      for (int s = 0; s < ns; ++s) {
+        const float* p = xs + (long long)s * T;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        long long t = 0;
+        const long long n = T - l;
+        for (; t + 3 < n; t += 4) {
+          a0 = fmaf(p[t], p[t + l], a0);
+          a1 = fmaf(p[t + 1], p[t + 1 + l], a1);
+          a2 = fmaf(p[t + 2], p[t + 2 + l], a2);
+          a3 = fmaf(p[t + 3], p[t + 3 + l], a3);
+        }
+        for (; t < n; ++t) a0 = fmaf(p[t], p[t + l], a0);
+        tot += (double)((a0 + a1) + (a2 + a3));
+      }
+    }
+    atomicAdd(&acov[(long long)l * D + d], tot / (double)T);
+  }
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" {
+
+int gb200_rhat_partial(const void* samples, int64_t T, int64_t C, int32_t D, double* stats, int32_t dtype, void* stream) {
+  if (!samples || !stats || T < 2 || C < 1 || D < 1) { set_error("rhat_partial: bad argument (need T >= 2)"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (dtype != GB200_F32 && dtype != GB200_F64) { set_error("rhat_partial: bad dtype"); return GB200_ERR_INVALID_ARGUMENT; }
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(stats, 0, sizeof(double) * (3 * D + 1), s);
+  const int block = 256;
+  long long want = (C * D + block - 1) / block;
+  int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+  if ((long long)grid * block < D) grid = (D + block - 1) / block;
+  const size_t sh = sizeof(double) * 3 * D;
+  if (dtype == GB200_F32) k_rhat_partial<float><<<grid, block, sh, s>>>((const float*)samples, T, C, D, stats);
+  else k_rhat_partial<double><<<grid, block, sh, s>>>((const double*)samples, T, C, D, stats);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+
+int gb200_rhat_finalize(const double* st, int64_t T, int32_t D, double* rhat) {
+  if (!st || !rhat || T < 2 || D < 1) { set_error("rhat_finalize: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
+  const double C = st[3 * D];
+  if (C < 2) { set_error("potential_scale_reduction as implemented only works for two or more chains."); return GB200_ERR_INVALID_ARGUMENT; }
+  for (int d = 0; d < D; ++d) {
+    const double m = st[d] / C;
+    const double var_means = (st[D + d] - C * m * m) / (C - 1.0);
+    const double B = (double)T * var_means;
+    const double W = st[2 * D + d] / C;
+    rhat[d] = sqrt((B / W + (double)T - 1.0) / (double)T);
+  }
+  return GB200_OK;
+}
+
+int gb200_ess_partial(const void* samples, int64_t T, int64_t C, int32_t D, int32_t num_lags, double* acov,
+                      int32_t dtype, void* stream) {
+  if (!samples || !acov || T < 2 || C < 1 || D < 1 || num_lags < 1) { set_error("ess_partial: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (dtype != GB200_F32 && dtype != GB200_F64) { set_error("ess_partial: bad dtype"); return GB200_ERR_INVALID_ARGUMENT; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (num_lags > T) num_lags = (int32_t)T;
+  cudaMemsetAsync(acov, 0, sizeof(double) * (size_t)num_lags * D, s);
+  const size_t max_sh = 200 * 1024;
+  long long S = (long long)(max_sh / (sizeof(float) * (size_t)T));
+  if (S < 1) { set_error("ess_partial: T=%lld too long for the shared-memory series tile", (long long)T); return GB200_ERR_UNSUPPORTED; }
+  if (S > 32) S = 32;
+  if (S > C) S = C;
+  const size_t sh = sizeof(float) * (size_t)S * (size_t)T;
+  dim3 grid((unsigned)((C + S - 1) / S), (unsigned)D);
+  const int block = 256;
+  cudaError_t e;
+  if (dtype == GB200_F32) {
+    e = cudaFuncSetAttribute(k_ess_partial<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e == cudaSuccess) k_ess_partial<float><<<grid, block, sh, s>>>((const float*)samples, T, C, D, num_lags, (int)S, acov);
+  } else {
+    e = cudaFuncSetAttribute(k_ess_partial<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e == cudaSuccess) k_ess_partial<double><<<grid, block, sh, s>>>((const double*)samples, T, C, D, num_lags, (int)S, acov);
+  }
+  if (e != cudaSuccess) { set_error("ess_partial: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+
+// Geyer initial positive + monotone sequence on the chain-averaged autocovariance
+// (diagnostics.py:133-209), restricted to the lags that were computed.
+int gb200_ess_finalize(const double* acov, const double* st, int64_t T, int64_t Ctot, int32_t D, int32_t num_lags,
+                       double* ess, uint8_t* truncated) {
+  if (!acov || !st || !ess || T < 4 || Ctot < 2 || D < 1 || num_lags < 2) { set_error("ess_finalize: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (num_lags > T) num_lags = (int32_t)T;
+  const double N = (double)T, M = (double)Ctot;
+  const long long n_even = T - T % 2;
+  long long L = num_lags < n_even ? num_lags : n_even;
+  L -= L % 2;
+  const long long P = L / 2;       // number of (even, odd) pairs available
+  const long long P_full = n_even / 2;
+  std::vector<double> even(P), odd(P);
+  std::vector<char> mask(P);
+  for (int d = 0; d < D; ++d) {
+    const double m = st[d] / M;
+    const double var_means = (st[D + d] - M * m * m) / (M - 1.0);
+    const double a0 = acov[d] / M;
+    const double mean_var0 = a0 * N / (N - 1.0);
+    const double weighted = mean_var0 * (N - 1.0) / N + var_means;
+    for (long long k = 0; k < L; ++k) {
+      const double rho = k == 0 ? 1.0 : 1.0 - (mean_var0 - acov[k * D + d] / M) / weighted;
+      if (k % 2 == 0) even[k / 2] = rho; else odd[k / 2] = rho;
+    }
+    bool carry = true;
+    long long max_t = 0;
+    for (long long t = 0; t < P; ++t) {
+      carry = carry && (even[t] + odd[t] > 0.0);
+      if (carry) max_t = t;
+      mask[t] = carry;
+    }
+    const bool trunc = carry && P < P_full;  // still positive at the last computed pair
+    if (truncated) truncated[d] = trunc;
+    // JAX: gather clamps out-of-bounds, scatter drops them
+    const bool in_bounds = (max_t + 1) < P_full;
+    const long long idx = (max_t + 1) < P ? (max_t + 1) : (P - 1);
+    const double even_at_idx_raw = even[idx];
+    for (long long t = 0; t < P; ++t) if (!mask[t]) odd[t] = 0.0;
+    for (long long t = 0; t < P; ++t) {
+      bool me = mask[t];
+      if (t == idx && in_bounds && (max_t + 1) < P) me = even_at_idx_raw > 0.0;
+      if (!me) even[t] = 0.0;
+    }
+    double prev = even[0] + odd[0];
+    for (long long t = 0; t < P; ++t) {
+      const double s = even[t] + odd[t];
+      if (s > prev) { even[t] = prev / 2.0; odd[t] = prev / 2.0; }
+      else prev = s;
+    }
+    double sum = 0.0;
+    for (long long t = 0; t < P; ++t) sum += even[t] + odd[t];
+    double tau = -1.0 + 2.0 * sum - even[idx];
+    const double ess_raw = M * N;
+    const double floor_tau = 1.0 / log10(ess_raw);
+    if (tau < floor_tau) tau = floor_tau;
+    ess[d] = ess_raw / tau;
+  }
+  return GB200_OK;
+}
+
+// Algorithmic FP32 flops per chain per integrator step of the closed-form algorithm
+// (FMA = 2; one per div/sqrt/exp/log).  Derivation in DESIGN.md "Roofline accounting".
+double gb200_flops_per_chain_step(int32_t sampler, const gb200_target_desc* t) {
+  if (!t) return 0.0;
+  const double D = t->D;
+  if (t->kind == GB200_TARGET_FUNNEL) {
+    switch (sampler) {
+      case GB200_LMCMONGE: return 59.0 * D + 60.0;
+      case GB200_LMC: return 92.0 * D + 140.0;
+      case GB200_RMHMC: return 0.0;  // depends on fixed-point iterations; reported per f-eval separately
+    }
+  }
+  return 0.0;
+}
+
+}  // extern "C"

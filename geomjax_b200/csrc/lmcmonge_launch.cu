@@ -1,0 +1,39 @@
+#include "lmcmonge.cuh"
+#include "launch.h"
+
+namespace gb {
+
+template <typename R, class Target>
+static int launch_lmcmonge_t(const TransArgs& a, const Target& tg, LayoutChoice lay, cudaStream_t s) {
+  int grid, block;
+  launch_shape(a.C, lay.lpc, &grid, &block);
+#define GB_X(E, L)                                                        \
+  if (lay.epl == E && lay.lpc == L) {                                     \
+    lmcmonge_kernel<R, Target, E, L><<<grid, block, 0, s>>>(a, tg);       \
+    GB_CHECK_LAUNCH();                                                    \
+    return GB200_OK;                                                      \
+  }
+  GB_MY_LAYOUTS(GB_X)
+#undef GB_X
+  set_error("lmcmonge: no kernel for layout (%d,%d)", lay.epl, lay.lpc);
+  return GB200_ERR_UNSUPPORTED;
+}
+
+int GB_LPC_NAME(launch_lmcmonge)(const TransArgs& a, const gb200_target_desc& t, LayoutChoice lay, int dtype, cudaStream_t s) {
+  if (dtype != GB200_F32) {
+    set_error("lmcmonge: only float32 is built in this version");
+    return GB200_ERR_UNSUPPORTED;
+  }
+  switch (t.kind) {
+    case GB200_TARGET_FUNNEL: {
+      Funnel<float> tg;
+      tg.setup(t);
+      return launch_lmcmonge_t<float>(a, tg, lay, s);
+    }
+    default:
+      set_error("lmcmonge: target kind %d has no in-kernel implementation", t.kind);
+      return GB200_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace gb

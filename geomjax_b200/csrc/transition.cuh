@@ -1,0 +1,119 @@
+// Pieces shared by the three fused transition kernels: argument block, per-chain key
+// derivation, noise draw, Metropolis-Hastings accept, dual-averaging epilogue.
+#pragma once
+#include "targets.cuh"
+
+namespace gb {
+
+// POD argument block (passed by value; built by api.cu from the C-ABI structs).
+struct TransArgs {
+  // state in / out (field-wise aliasing allowed)
+  const void *in_pos, *in_logp, *in_grad, *in_vol;
+  void *out_pos, *out_logp, *out_grad, *out_vol;
+  gb200_info info;
+  gb200_run_opts opts;
+  gb200_key_source ks;
+  // kernel params
+  double step_size;
+  const void* step_size_per_chain;
+  const void* inv_mass;
+  double alpha2;
+  double divergence_threshold;
+  double fp_tol, fp_div_tol;
+  int fp_max_iters;
+  int num_steps;
+  int half_step;
+  int D;
+  int metric;  // gb200_metric_kind
+  int mode;    // gb200_threefry_mode
+  long long C;
+};
+
+__device__ __forceinline__ U2 transition_key(const TransArgs& a, long long chain, long long t) {
+  if (a.ks.keys != nullptr) {
+    return U2{a.ks.keys[2 * chain], a.ks.keys[2 * chain + 1]};
+  }
+  U2 root{a.ks.root_key[0], a.ks.root_key[1]};
+  return chain_key(a.mode, root, (uint32_t)a.ks.total_transitions, (uint32_t)t,
+                         (uint32_t)a.ks.total_chains, (uint32_t)(a.ks.chain_offset + chain));
+}
+
+// z = jax.random.normal(key, (D,)) distributed over the lane group (util.py:81-82).
+template <typename R, int EPL, int LPC>
+__device__ __forceinline__ void draw_noise(const TransArgs& a, const Lay<EPL, LPC>& lay, U2 key,
+                                           long long chain, R (&z)[EPL]) {
+  if (a.opts.noise_override != nullptr) {
+    const R* zo = (const R*)a.opts.noise_override + chain * a.D;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) z[k] = lay.valid(k) ? zo[lay.j(k)] : R(0);
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) {
+    z[k] = R(0);
+    if (lay.valid(k)) z[k] = (R)bits_to_normal(random_bits_elem(a.mode, key, (uint32_t)lay.j(k), (uint32_t)a.D));
+  }
+}
+
+// mcmc/proposal.py:87-121 (proposal_from_energy_diff) + :168-185 (static_binomial_sampling)
+template <typename R>
+struct MH {
+  R weight, p_accept, u;
+  bool accept, divergent;
+};
+
+template <typename R>
+__device__ __forceinline__ MH<R> metropolis(const TransArgs& a, U2 key_accept, long long chain, R H0, R H1) {
+  MH<R> m;
+  R delta = H0 - H1;
+  if (isnan(delta)) delta = -Lim<R>::inf();
+  m.weight = delta;
+  m.p_accept = fmin(exp(delta), R(1));
+  m.divergent = (-delta) > (R)a.divergence_threshold;
+  if (a.opts.uniform_override != nullptr) m.u = ((const R*)a.opts.uniform_override)[chain];
+  else m.u = (R)uniform_scalar(a.mode, key_accept);
+  m.accept = m.u < m.p_accept;
+  return m;
+}
+
+// optimizers/dual_averaging.py:101-123 applied to gradient = target - acceptance_rate
+template <typename R>
+__device__ __forceinline__ void dual_averaging_update(R* da, R accept_rate, R target, R t0, R gamma, R kappa) {
+  const R log_step = da[0], avg_log_step = da[1], step = da[2], avg_err0 = da[3], mu = da[4];
+  const R reg_step = step + t0;
+  const R eta = pow(step, -kappa);
+  const R avg_err = (R(1) - R(1) / reg_step) * avg_err0 + (target - accept_rate) / reg_step;
+  da[0] = mu - (sqrt(step) / gamma) * avg_err;
+  da[1] = eta * log_step + (R(1) - eta) * avg_log_step;
+  da[2] = step + R(1);
+  da[3] = avg_err;
+}
+
+template <typename R, int EPL, int LPC>
+__device__ __forceinline__ void load_vec(const Lay<EPL, LPC>& lay, const void* base, long long chain, R (&v)[EPL]) {
+  const R* p = (const R*)base + chain * lay.D;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) v[k] = lay.valid(k) ? p[lay.j(k)] : R(0);
+}
+template <typename R, int EPL, int LPC>
+__device__ __forceinline__ void store_vec(const Lay<EPL, LPC>& lay, void* base, long long chain, const R (&v)[EPL], R sign = R(1)) {
+  if (base == nullptr) return;
+  R* p = (R*)base + chain * lay.D;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k)
+    if (lay.valid(k)) p[lay.j(k)] = sign * v[k];
+}
+template <typename R>
+__device__ __forceinline__ void store_scalar(void* base, long long chain, R v) {
+  if (base != nullptr) ((R*)base)[chain] = v;
+}
+
+template <typename R, int EPL, int LPC>
+__device__ __forceinline__ R dotv(const R (&a)[EPL], const R (&b)[EPL]) {
+  R s = R(0);
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) s += a[k] * b[k];
+  return s;
+}
+
+}  // namespace gb

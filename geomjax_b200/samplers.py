@@ -1,0 +1,389 @@
+"""rmhmc / lmc / lmcmonge with the reference's ``build_kernel / init / step`` API, batched over a
+leading chain axis and executed by the fused CUDA kernels behind the C ABI.
+
+Mirrors (names, argument order, defaults, NamedTuple fields):
+  geomjax/rmhmc/rmhmc.py:30-41,58-93,96-98,110-176,247-311
+  geomjax/lmcmc/lmc.py:30-42,60-95,98-101,114-182,255-346
+  geomjax/lmcmonge/lmc.py:32-44,63-98,101-109,130-237,312-405
+  geomjax/mcmc/proposal.py:22-40 (Proposal)
+Differences, all forced by "no tracing compiler, no CPU fallback":
+  * ``logdensity_fn`` / ``metric_fn`` are ``TargetDescriptor`` objects (geomjax_b200.targets);
+  * every array carries a leading chain axis: ``init(position[C, D])``,
+    ``step(rng_keys[C, 2] uint32, state)`` == ``jax.vmap(kernel)(keys, states)``
+    (examples/funnel/main.py:13,19);
+  * ``integrator`` must be one of the sentinels in ``geomjax_b200.integrators``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import integrators
+from . import random as grandom
+from .base import SamplingAlgorithm
+from .targets import as_target
+
+__all__ = ["rmhmc", "lmc", "lmcmonge", "RMHMCState", "RMHMCInfo", "LMCState", "LMCInfo", "Proposal",
+           "run_fused"]
+
+
+class RMHMCState(NamedTuple):
+    position: torch.Tensor
+    logdensity: torch.Tensor
+    logdensity_grad: torch.Tensor
+
+
+class LMCState(NamedTuple):
+    position: torch.Tensor
+    logdensity: torch.Tensor
+    logdensity_grad: torch.Tensor
+    volume_adjustment: torch.Tensor
+
+
+class RMHMCIntegratorState(NamedTuple):  # rmhmc/integrators.py:25-36
+    position: torch.Tensor
+    momentum: torch.Tensor
+    velocity: torch.Tensor
+    logdensity: torch.Tensor
+    logdensity_grad: torch.Tensor
+
+
+class LMCIntegratorState(NamedTuple):  # lmcmc/integrators.py:26-38
+    position: torch.Tensor
+    momentum: torch.Tensor
+    velocity: torch.Tensor
+    logdensity: torch.Tensor
+    logdensity_grad: torch.Tensor
+    volume_adjustment: torch.Tensor
+
+
+class Proposal(NamedTuple):  # mcmc/proposal.py:22-40
+    state: NamedTuple
+    energy: torch.Tensor
+    weight: torch.Tensor
+    sum_log_p_accept: torch.Tensor
+
+
+class RMHMCInfo(NamedTuple):
+    momentum: torch.Tensor
+    acceptance_rate: torch.Tensor
+    is_accepted: torch.Tensor
+    is_divergent: torch.Tensor
+    energy: torch.Tensor
+    proposal: Proposal
+    num_integration_steps: int
+
+
+class LMCInfo(NamedTuple):
+    velocity: torch.Tensor
+    acceptance_rate: torch.Tensor
+    is_accepted: torch.Tensor
+    is_divergent: torch.Tensor
+    energy: torch.Tensor
+    proposal: Proposal
+    num_integration_steps: int
+
+
+# ------------------------------------------------------------------------------------ engine
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return N.F32
+    if t.dtype == torch.float64:
+        return N.F64
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _check_position(position, target):
+    if not isinstance(position, torch.Tensor):
+        raise TypeError("position must be a torch tensor on a CUDA device, shape (C, D)")
+    if position.ndim != 2 or position.shape[1] != target.D:
+        raise ValueError(f"position must have shape (C, {target.D}); got {tuple(position.shape)}")
+    if not position.is_cuda:
+        raise N.NativeError("geomjax_b200 operates on CUDA tensors only (no CPU fallback)")
+    return position.contiguous()
+
+
+def _init(position, logdensity_fn, with_volume: bool):
+    target = as_target(logdensity_fn)
+    q = _check_position(position, target)
+    C_ = q.shape[0]
+    logp = torch.empty(C_, dtype=q.dtype, device=q.device)
+    grad = torch.empty_like(q)
+    vol = torch.empty(C_, dtype=q.dtype, device=q.device) if with_volume else None
+    st = N.State(N.ptr(q), N.ptr(logp), N.ptr(grad), N.ptr(vol))
+    desc = target.c_struct()
+    with torch.cuda.device(q.device):
+        N.check(N.lib().gb200_init(C.byref(desc), st, C_, _dtype_code(q), N.stream_ptr()))
+    return (q, logp, grad, vol)
+
+
+class _Engine:
+    """One configured transition kernel (sampler id + target + parameters)."""
+
+    def __init__(self, sampler: int, target, step_size, num_integration_steps, *,
+                 divergence_threshold=1000, inverse_mass_matrix=None, alpha2=0.001,
+                 half_step="omega", fp_convergence_tol=1e-6, fp_divergence_tol=1e10, fp_max_iters=100,
+                 lanes_per_chain=0):
+        self.sampler = sampler
+        self.target = as_target(target)
+        self.step_size = step_size
+        self.L = int(num_integration_steps)
+        self.divergence_threshold = float(divergence_threshold)
+        self.inverse_mass_matrix = inverse_mass_matrix
+        self.alpha2 = float(alpha2)
+        self.half_step = N.HALF_STEP[half_step]
+        self.fp = (float(fp_convergence_tol), float(fp_divergence_tol), int(fp_max_iters))
+        self.lanes_per_chain = int(lanes_per_chain)
+        self.with_volume = sampler != N.RMHMC
+
+    def _params(self, ref: torch.Tensor):
+        p = N.KernelParams()
+        keep = []
+        ss = self.step_size
+        if isinstance(ss, torch.Tensor) and ss.ndim >= 1:
+            ss = ss.to(device=ref.device, dtype=ref.dtype).contiguous()
+            if ss.shape != (ref.shape[0],):
+                raise ValueError("per-chain step_size must have shape (C,)")
+            p.step_size_per_chain = N.ptr(ss)
+            keep.append(ss)
+            p.step_size = 0.0
+        else:
+            p.step_size = float(ss)
+        p.num_integration_steps = self.L
+        p.threefry_mode = grandom.threefry_mode()
+        p.divergence_threshold = self.divergence_threshold
+        p.fp_convergence_tol, p.fp_divergence_tol, p.fp_max_iters = self.fp
+        p.half_step = self.half_step
+        p.alpha2 = self.alpha2
+        if self.inverse_mass_matrix is not None:
+            im = self.inverse_mass_matrix
+            if isinstance(im, np.ndarray):
+                im = torch.from_numpy(im)
+            im = im.to(device=ref.device, dtype=ref.dtype).contiguous()
+            if im.ndim != 1:
+                # lmcmonge/metrics.py:145-153: only a diagonal (1-d) mass matrix is accepted
+                raise ValueError("The mass matrix has the wrong number of dimensions:"
+                                 f" expected 1, got {im.ndim}.")
+            if im.shape[0] != self.target.D:
+                raise ValueError("inverse_mass_matrix must have shape (D,)")
+            p.inverse_mass_matrix = N.ptr(im)
+            keep.append(im)
+        p.dtype = _dtype_code(ref)
+        p.lanes_per_chain = self.lanes_per_chain
+        return p, keep
+
+    def launch(self, state, key_source: N.KeySource, *, want_info=True, out_state=None, opts=None,
+               extra_info=False):
+        q = _check_position(state[0], self.target)
+        C_, D = q.shape
+        dev, dt = q.device, q.dtype
+        fields = [q] + [t.contiguous() for t in state[1:]]
+        if out_state is None:
+            out = [torch.empty_like(t) for t in fields]
+        else:
+            out = list(out_state)
+        if not self.with_volume:
+            fields = fields[:3] + [None]
+            out = out[:3] + [None]
+        st_in = N.State(*[N.ptr(t) for t in fields])
+        st_out = N.State(*[N.ptr(t) for t in out])
+        info_c = N.Info()
+        info_t = {}
+        if want_info:
+            def new(name, shape, dtype=dt):
+                t = torch.empty(shape, dtype=dtype, device=dev)
+                info_t[name] = t
+                setattr(info_c, name, N.ptr(t))
+            new("momentum", (C_, D)); new("acceptance_rate", (C_,))
+            new("is_accepted", (C_,), torch.uint8); new("is_divergent", (C_,), torch.uint8)
+            new("energy", (C_,)); new("proposal_position", (C_, D)); new("proposal_momentum", (C_, D))
+            new("proposal_velocity", (C_, D)); new("proposal_logdensity", (C_,))
+            new("proposal_logdensity_grad", (C_, D)); new("proposal_weight", (C_,))
+            if self.with_volume:
+                new("proposal_volume_adjustment", (C_,))
+            if extra_info:
+                new("initial_energy", (C_,)); new("accept_uniform", (C_,)); new("noise", (C_, D))
+                if self.sampler == N.RMHMC:
+                    new("fp_iters", (C_,), torch.int32)
+        p, keep = self._params(q)
+        desc = self.target.c_struct()
+        with torch.cuda.device(dev):
+            N.check(N.lib().gb200_step(self.sampler, C.byref(p), C.byref(desc), C.byref(key_source), st_in, st_out,
+                                       C.byref(info_c) if want_info else None,
+                                       C.byref(opts) if opts is not None else None, C_, N.stream_ptr()))
+        return out, info_t
+
+    # -- public pieces ---------------------------------------------------------------
+    def make_state(self, fields):
+        return LMCState(*fields) if self.with_volume else RMHMCState(*fields[:3])
+
+    def make_info(self, t):
+        if self.with_volume:
+            ist = LMCIntegratorState(t["proposal_position"], t["proposal_momentum"], t["proposal_velocity"],
+                                     t["proposal_logdensity"], t["proposal_logdensity_grad"],
+                                     t["proposal_volume_adjustment"])
+            cls = LMCInfo
+        else:
+            ist = RMHMCIntegratorState(t["proposal_position"], t["proposal_momentum"], t["proposal_velocity"],
+                                       t["proposal_logdensity"], t["proposal_logdensity_grad"])
+            cls = RMHMCInfo
+        w = t["proposal_weight"]
+        prop = Proposal(ist, t["energy"], w, torch.clamp(w, max=0.0))
+        return cls(t["momentum"], t["acceptance_rate"], t["is_accepted"].bool(), t["is_divergent"].bool(),
+                   t["energy"], prop, self.L)
+
+    def step(self, rng_key, state):
+        keys = grandom._keys_tensor(rng_key, state[0].device)
+        if keys.shape != (state[0].shape[0], 2):
+            raise ValueError(f"rng_key must have shape (C, 2) = ({state[0].shape[0]}, 2); got {tuple(keys.shape)} "
+                             "(one key per chain, as in jax.vmap(kernel)(keys, states))")
+        ks = N.KeySource()
+        ks.keys = N.ptr(keys)
+        ks.num_transitions = 1
+        out, info = self.launch(state, ks, want_info=True)
+        return self.make_state(out), self.make_info(info)
+
+
+class _StepFn:
+    """``SamplingAlgorithm.step``; also exposes the fused multi-transition launch."""
+
+    def __init__(self, engine: _Engine):
+        self.engine = engine
+
+    def __call__(self, rng_key, state):
+        return self.engine.step(rng_key, state)
+
+
+def run_fused(step_fn, rng_key, state, num_samples: int, *, first: int = 0, total: Optional[int] = None,
+              chain_offset: int = 0, total_chains: Optional[int] = None, return_samples: bool = False,
+              return_accept: bool = False, dual_averaging=None, da_target: float = 0.8):
+    """Run ``num_samples`` transitions in ONE launch with in-kernel key derivation
+    ``split(split(rng_key, total)[t], total_chains)[chain_offset + c]`` -- the driver loop of
+    examples/funnel/main.py:7-25 (``inference_loop_multiple_chains``) without the host round trip.
+    Identical, bit for bit, to calling ``step`` ``num_samples`` times with those keys.
+    Returns (state, samples[T, C, D] | None, acceptance_rate[T, C] | None)."""
+    eng = step_fn.engine if isinstance(step_fn, _StepFn) else step_fn
+    q = state[0]
+    C_, D = q.shape
+    total = num_samples + first if total is None else total
+    total_chains = C_ + chain_offset if total_chains is None else total_chains
+    ks = N.KeySource()
+    ks.keys = None
+    ks.root_key[0], ks.root_key[1] = int(rng_key[0]), int(rng_key[1])
+    ks.first_transition, ks.num_transitions, ks.total_transitions = first, num_samples, total
+    ks.chain_offset, ks.total_chains = chain_offset, total_chains
+    opts = N.RunOpts()
+    samples = acc = None
+    if return_samples:
+        samples = torch.empty((num_samples, C_, D), dtype=q.dtype, device=q.device)
+        opts.samples = N.ptr(samples)
+    if return_accept:
+        acc = torch.empty((num_samples, C_), dtype=q.dtype, device=q.device)
+        opts.sample_accept = N.ptr(acc)
+    if dual_averaging is not None:
+        opts.dual_averaging = N.ptr(dual_averaging)
+        opts.da_target, opts.da_t0, opts.da_gamma, opts.da_kappa = da_target, 10.0, 0.05, 0.75
+    out, _ = eng.launch(state, ks, want_info=False, opts=opts)
+    return eng.make_state(out), samples, acc
+
+
+# ------------------------------------------------------------------------------------ façades
+
+
+def _kernel_fn(sampler_id, kind):
+    """build_kernel(...) -> kernel(rng_key, state, logdensity_fn, step_size, metric_fn|inverse_mass_matrix,
+    num_integration_steps[, alpha2])."""
+
+    def build_kernel(integrator: Callable = None, divergence_threshold: float = 1000):
+        default = {N.RMHMC: integrators.implicit_midpoint, N.LMC: integrators.lan_integrator,
+                   N.LMCMONGE: integrators.lan_integrator_monge}[sampler_id]
+        integ = integrators.resolve(default if integrator is None else integrator, sampler_id)
+
+        if sampler_id == N.LMCMONGE:
+            def kernel(rng_key, state, logdensity_fn, step_size, inverse_mass_matrix, num_integration_steps,
+                       alpha2):
+                eng = _Engine(sampler_id, logdensity_fn, step_size, num_integration_steps,
+                              divergence_threshold=divergence_threshold, inverse_mass_matrix=inverse_mass_matrix,
+                              alpha2=alpha2, **integ.kwargs)
+                return eng.step(rng_key, state)
+        else:
+            def kernel(rng_key, state, logdensity_fn, step_size, metric_fn, num_integration_steps):
+                tgt = _merge_target(logdensity_fn, metric_fn)
+                eng = _Engine(sampler_id, tgt, step_size, num_integration_steps,
+                              divergence_threshold=divergence_threshold, **integ.kwargs)
+                return eng.step(rng_key, state)
+        return kernel
+
+    return build_kernel
+
+
+def _merge_target(logdensity_fn, metric_fn):
+    t = as_target(logdensity_fn)
+    if metric_fn is None or metric_fn is t:
+        return t
+    if isinstance(metric_fn, str):
+        return t.with_metric(metric_fn)
+    m = as_target(metric_fn)
+    if (m.kind, m.D, m.params) != (t.kind, t.D, t.params):
+        raise ValueError("metric_fn must be the metric of the same target descriptor (or 'identity')")
+    return m
+
+
+class rmhmc:
+    """geomjax/rmhmc/rmhmc.py:247-311."""
+
+    @staticmethod
+    def init(position, logdensity_fn):
+        return RMHMCState(*_init(position, logdensity_fn, False)[:3])
+
+    build_kernel = staticmethod(_kernel_fn(N.RMHMC, "rmhmc"))
+
+    def __new__(cls, logdensity_fn, step_size, metric_fn, num_integration_steps, *,
+                divergence_threshold: int = 1000, integrator: Callable = None, lanes_per_chain: int = 0):
+        integ = integrators.resolve(integrators.implicit_midpoint if integrator is None else integrator, N.RMHMC)
+        eng = _Engine(N.RMHMC, _merge_target(logdensity_fn, metric_fn), step_size, num_integration_steps,
+                      divergence_threshold=divergence_threshold, lanes_per_chain=lanes_per_chain, **integ.kwargs)
+        return SamplingAlgorithm(lambda position: cls.init(position, eng.target), _StepFn(eng))
+
+
+class lmc:
+    """geomjax/lmcmc/lmc.py:255-346."""
+
+    @staticmethod
+    def init(position, logdensity_fn):
+        return LMCState(*_init(position, logdensity_fn, True))
+
+    build_kernel = staticmethod(_kernel_fn(N.LMC, "lmc"))
+
+    def __new__(cls, logdensity_fn, step_size, metric_fn, num_integration_steps, *,
+                divergence_threshold: int = 1000, integrator: Callable = None, lanes_per_chain: int = 0):
+        integ = integrators.resolve(integrators.lan_integrator if integrator is None else integrator, N.LMC)
+        eng = _Engine(N.LMC, _merge_target(logdensity_fn, metric_fn), step_size, num_integration_steps,
+                      divergence_threshold=divergence_threshold, lanes_per_chain=lanes_per_chain, **integ.kwargs)
+        return SamplingAlgorithm(lambda position: cls.init(position, eng.target), _StepFn(eng))
+
+
+class lmcmonge:
+    """geomjax/lmcmonge/lmc.py:312-405 (``alpha2=0.001`` default :385)."""
+
+    @staticmethod
+    def init(position, logdensity_fn):
+        return LMCState(*_init(position, logdensity_fn, True))
+
+    build_kernel = staticmethod(_kernel_fn(N.LMCMONGE, "lmcmonge"))
+
+    def __new__(cls, logdensity_fn, step_size, inverse_mass_matrix, num_integration_steps, *,
+                alpha2: float = 0.001, divergence_threshold: int = 1000, integrator: Callable = None,
+                lanes_per_chain: int = 0):
+        integ = integrators.resolve(integrators.lan_integrator_monge if integrator is None else integrator,
+                                    N.LMCMONGE)
+        eng = _Engine(N.LMCMONGE, logdensity_fn, step_size, num_integration_steps,
+                      divergence_threshold=divergence_threshold, inverse_mass_matrix=inverse_mass_matrix,
+                      alpha2=alpha2, lanes_per_chain=lanes_per_chain, **integ.kwargs)
+        return SamplingAlgorithm(lambda position: cls.init(position, eng.target), _StepFn(eng))

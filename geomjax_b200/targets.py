@@ -1,0 +1,66 @@
+"""Target descriptors: the built-in replacements for the reference's ``logdensity_fn`` /
+``metric_fn`` callables (the engine evaluates targets inside the fused CUDA kernels, so an
+arbitrary Python callable cannot be accepted -- there is no CPU / tracing fallback).
+
+Only Neal's funnel exists in the reference tree (examples/funnel/main.py:28-54); the others
+are the NEW built-ins named by BASELINE.json's north_star.
+"""
+from __future__ import annotations
+
+from . import _native as N
+
+
+class TargetDescriptor:
+    """Opaque handle passed wherever the reference takes ``logdensity_fn`` (and ``metric_fn``)."""
+
+    def __init__(self, kind: int, D: int, params=(), metric: int = N.METRIC_TARGET, N_rows: int = 0,
+                 X=None, y=None, vec0=None, vec1=None, name: str = "target"):
+        self.kind, self.D, self.metric, self.name = int(kind), int(D), int(metric), name
+        self.params = tuple(float(p) for p in params)
+        self.N = int(N_rows)
+        self._keep = (X, y, vec0, vec1)  # keep the device tensors alive
+
+    def c_struct(self) -> N.TargetDesc:
+        d = N.TargetDesc()
+        d.kind, d.metric, d.D, d.N = self.kind, self.metric, self.D, self.N
+        for i, p in enumerate(self.params):
+            d.params[i] = p
+        X, y, v0, v1 = self._keep
+        d.X, d.y, d.vec0, d.vec1 = N.ptr(X), N.ptr(y), N.ptr(v0), N.ptr(v1)
+        return d
+
+    def with_metric(self, metric: str) -> "TargetDescriptor":
+        """``metric='identity'`` == ``metric_fn=lambda x: jnp.eye(D)`` (tests/test_samplers.py:25)."""
+        m = {"target": N.METRIC_TARGET, "identity": N.METRIC_IDENTITY}[metric]
+        t = TargetDescriptor(self.kind, self.D, self.params, m, self.N, *self._keep, name=self.name)
+        return t
+
+    # the reference passes the same object's bound methods as logdensity_fn / metric_fn
+    @property
+    def logp(self):
+        return self
+
+    @property
+    def fisher_metric_fn(self):
+        return self
+
+    metric_fn = fisher_metric_fn
+
+    def __repr__(self):
+        return f"TargetDescriptor({self.name}, D={self.D})"
+
+
+def neal_funnel(D: int = 2, mean: float = 0.0, sigma: float = 3.0) -> TargetDescriptor:
+    """examples/funnel/main.py:28-54 (``class neal_funnel``); ``mean`` is unused there as well."""
+    if D < 2:
+        raise ValueError("neal_funnel needs D >= 2")
+    return TargetDescriptor(N.TARGET_FUNNEL, D, (sigma,), name="neal_funnel")
+
+
+def as_target(obj) -> TargetDescriptor:
+    if isinstance(obj, TargetDescriptor):
+        return obj
+    raise NotImplementedError(
+        "geomjax_b200 evaluates log-densities and metrics inside fused CUDA kernels: pass a "
+        "TargetDescriptor (e.g. geomjax_b200.targets.neal_funnel(D)) where the reference takes "
+        f"logdensity_fn / metric_fn; got {type(obj).__name__}. There is no CPU fallback.")

@@ -1,0 +1,224 @@
+/* geomb200.h -- C ABI of the B200-native batched-chain engine for geomjax's static
+ * Riemannian transition kernels (rmhmc, lmc, lmcmonge).
+ *
+ * The reference (williwilliams3/geomjax) has no FFI layer: its operator API is Python
+ *   geomjax.rmhmc / lmc / lmcmonge (logdensity_fn, step_size, metric_fn | inverse_mass_matrix,
+ *                                   num_integration_steps, ...) -> SamplingAlgorithm(init, step)
+ *   (geomjax/rmhmc/rmhmc.py:286-311, geomjax/lmcmc/lmc.py:321-346, geomjax/lmcmonge/lmc.py:378-405)
+ * and users batch it with jax.vmap(kernel)(keys, states) (examples/funnel/main.py:13,19).
+ * Each entry point below is what a typed-FFI custom call for that path would bind; the
+ * reference interface it replaces is cited on every declaration.  INTEGRATION.md shows the
+ * jax.ffi and ctypes stubs.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every buffer is caller-owned DEVICE memory,
+ *     row-major (C, D) like the vmapped JAX arrays, float32 (dtype GB200_F32) unless stated;
+ *   - every call is asynchronous on the caller's cudaStream_t (passed as void*), never
+ *     synchronises and never allocates;
+ *   - returns 0 on success or a negative gb200_status; the message is available through
+ *     gb200_last_error() (thread-local).  Numerical failures (NaN energy, divergence,
+ *     fixed-point non-convergence) are DATA reported in gb200_info, never error codes
+ *     (mcmc/proposal.py:107-108, rmhmc/rmhmc.py:424);
+ *   - re-entrant, no global mutable state besides the thread-local error string.
+ */
+#ifndef GEOMB200_H
+#define GEOMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB200_VERSION 100
+
+typedef enum gb200_status {
+  GB200_OK = 0,
+  GB200_ERR_INVALID_ARGUMENT = -1,
+  GB200_ERR_UNSUPPORTED = -2,
+  GB200_ERR_CUDA = -3
+} gb200_status;
+
+typedef enum gb200_dtype { GB200_F32 = 0, GB200_F64 = 1 } gb200_dtype;
+
+/* jax_threefry_partitionable=False ("legacy", the reference's effective JAX range) or True. */
+typedef enum gb200_threefry_mode { GB200_THREEFRY_LEGACY = 0, GB200_THREEFRY_PARTITIONABLE = 1 } gb200_threefry_mode;
+
+typedef enum gb200_sampler { GB200_RMHMC = 0, GB200_LMC = 1, GB200_LMCMONGE = 2 } gb200_sampler;
+
+/* lmcmonge/integrators.py:158-194 as written ("omega", default), the same with the
+ * missing alpha2 restored ("omega_fixed"), and :197-230 ("omegatilde"). */
+typedef enum gb200_half_step { GB200_HALF_STEP_OMEGA = 0, GB200_HALF_STEP_OMEGA_FIXED = 1, GB200_HALF_STEP_OMEGATILDE = 2 } gb200_half_step;
+
+/* Built-in targets: replace the reference's logdensity_fn / metric_fn callables
+ * (examples/funnel/main.py:28-54 is the only instance in the reference tree). */
+typedef enum gb200_target_kind {
+  GB200_TARGET_FUNNEL = 0,   /* Neal's funnel, pull-back ("fisher_metric_fn") metric; params[0]=sigma */
+  GB200_TARGET_GAUSSIAN = 1, /* diagonal Gaussian; vec0=mean[D], vec1=precision[D]; metric=diag(precision) */
+  GB200_TARGET_BANANA = 2,   /* D=2; params[0]=sigma1^2, params[1]=b; identity metric */
+  GB200_TARGET_LOGREG = 3    /* Bayesian logistic regression; X[N,D] row-major, y[N]; params[0]=prior precision; Fisher+prior metric */
+} gb200_target_kind;
+
+typedef enum gb200_metric_kind {
+  GB200_METRIC_TARGET = 0,   /* the target's own Riemannian metric */
+  GB200_METRIC_IDENTITY = 1  /* metric_fn = lambda x: eye(D) (tests/test_samplers.py:25,37) */
+} gb200_metric_kind;
+
+typedef struct gb200_target_desc {
+  int32_t kind;          /* gb200_target_kind */
+  int32_t metric;        /* gb200_metric_kind */
+  int32_t D;
+  int32_t reserved;
+  int64_t N;             /* data rows (logreg) */
+  double params[8];
+  const void* X;         /* borrowed device pointers; must outlive every call using the descriptor */
+  const void* y;
+  const void* vec0;
+  const void* vec1;
+} gb200_target_desc;
+
+/* kwargs of the reference kernels: rmhmc/rmhmc.py:286-311 (+ solver kwargs of
+ * rmhmc/integrators.py:53-61), lmcmc/lmc.py:321-346, lmcmonge/lmc.py:378-405. */
+typedef struct gb200_kernel_params {
+  double step_size;                  /* scalar step size, used when step_size_per_chain == NULL */
+  const void* step_size_per_chain;   /* optional [C] (vmapped adaptation); dtype of the call */
+  int32_t num_integration_steps;
+  int32_t threefry_mode;             /* gb200_threefry_mode */
+  double divergence_threshold;       /* default 1000 */
+  double fp_convergence_tol;         /* rmhmc: default 1e-6 */
+  double fp_divergence_tol;          /* rmhmc: default 1e10 */
+  int32_t fp_max_iters;              /* rmhmc: default 100 */
+  int32_t half_step;                 /* lmcmonge: gb200_half_step */
+  double alpha2;                     /* lmcmonge: default 1e-3 */
+  const void* inverse_mass_matrix;   /* lmcmonge: [D] diagonal, NULL = ones */
+  int32_t dtype;                     /* gb200_dtype */
+  int32_t lanes_per_chain;           /* 0 = auto; else 1,2,4,8,16,32 (tuning knob) */
+} gb200_kernel_params;
+
+/* RMHMCState / LMCState (rmhmc/rmhmc.py:30-41, lmcmc/lmc.py:30-42, lmcmonge/lmc.py:32-44). */
+typedef struct gb200_state {
+  void* position;          /* [C, D] */
+  void* logdensity;        /* [C] */
+  void* logdensity_grad;   /* [C, D] */
+  void* volume_adjustment; /* [C]; LMC kernels only, NULL for rmhmc */
+} gb200_state;
+
+/* RMHMCInfo / LMCInfo (rmhmc/rmhmc.py:58-93, lmcmc/lmc.py:60-95, lmcmonge/lmc.py:63-98).
+ * Every field may be NULL (not written). */
+typedef struct gb200_info {
+  void* momentum;            /* [C, D] initial draw: momentum (rmhmc) or velocity (lmc, lmcmonge) */
+  void* acceptance_rate;     /* [C] */
+  uint8_t* is_accepted;      /* [C] */
+  uint8_t* is_divergent;     /* [C] */
+  void* energy;              /* [C] energy of the proposed state */
+  void* proposal_position;   /* [C, D] info.proposal.state.position */
+  void* proposal_momentum;   /* [C, D] (flipped) */
+  void* proposal_velocity;   /* [C, D] (flipped) */
+  void* proposal_logdensity; /* [C] */
+  void* proposal_logdensity_grad; /* [C, D] */
+  void* proposal_volume_adjustment; /* [C] */
+  void* proposal_weight;     /* [C] H0 - H1 (NaN -> -inf) */
+  void* initial_energy;      /* [C] H0 (extra; not in the reference Info) */
+  int32_t* fp_iters;         /* [C] rmhmc: total fixed-point iterations over the trajectory (extra) */
+  void* accept_uniform;      /* [C] the uniform the accept test used (extra, test surface) */
+  void* noise;               /* [C, D] the standard normal draw z (extra, test surface) */
+} gb200_info;
+
+/* Where the per-chain keys of a transition come from.
+ *   keys != NULL : explicit per-chain keys [C, 2] uint32 == vmap(kernel)(keys, states);
+ *                  num_transitions must be 1.
+ *   keys == NULL : derived in-kernel exactly like the driver loop of
+ *                  examples/funnel/main.py:18,22: k = split(split(root, total_transitions)[t], total_chains)[chain_offset + c]
+ *                  for t = first_transition .. first_transition + num_transitions - 1 (fused launch). */
+typedef struct gb200_key_source {
+  const uint32_t* keys;
+  uint32_t root_key[2];
+  int64_t first_transition;
+  int64_t num_transitions;
+  int64_t total_transitions;
+  int64_t chain_offset;
+  int64_t total_chains;
+} gb200_key_source;
+
+/* Optional per-launch extras (all may be NULL / zero). */
+typedef struct gb200_run_opts {
+  void* samples;               /* [num_transitions, C, D] positions after each transition (examples/funnel/main.py:20) */
+  void* sample_accept;         /* [num_transitions, C] acceptance_rate per transition */
+  const void* noise_override;  /* [C, D] use this z instead of drawing (test surface, num_transitions==1) */
+  const void* uniform_override;/* [C] use this accept uniform (test surface, num_transitions==1) */
+  void* dual_averaging;        /* [C, 5] (log_x, log_x_avg, step, avg_error, mu): fused per-chain dual averaging
+                                  (optimizers/dual_averaging.py:101-123); step size = exp(log_x) */
+  double da_target;            /* target acceptance rate (adaptation/step_size_adaptation.py:103) */
+  double da_t0, da_gamma, da_kappa; /* (10, 0.05, 0.75) */
+} gb200_run_opts;
+
+int gb200_version(void);
+const char* gb200_last_error(void);
+
+/* ---- PRNG test surface: jax.random.split / bits / uniform / normal --------------------- */
+/* split(keys[n], num) -> out[n, num, 2]            (rmhmc/rmhmc.py:158 etc.) */
+int gb200_threefry_split(const uint32_t* keys, uint32_t* out, int64_t n_keys, int32_t num, int32_t mode, void* stream);
+/* random_bits(keys[n], (count,)) -> out[n, count] */
+int gb200_random_bits(const uint32_t* keys, uint32_t* out, int64_t n_keys, int32_t count, int32_t mode, void* stream);
+/* uniform(keys[n], (count,), float32) -> out[n, count]   (mcmc/proposal.py:178 via bernoulli) */
+int gb200_uniform_f32(const uint32_t* keys, float* out, int64_t n_keys, int32_t count, int32_t mode, void* stream);
+/* normal(keys[n], (count,), float32) -> out[n, count]    (util.py:81-82) */
+int gb200_normal_f32(const uint32_t* keys, float* out, int64_t n_keys, int32_t count, int32_t mode, void* stream);
+/* split(split(root, total_transitions)[t], total_chains)[chain_offset + c], c < C -> out[C, 2] */
+int gb200_chain_keys(const uint32_t root_key[2], int64_t t, int64_t total_transitions, int64_t chain_offset,
+                     int64_t total_chains, uint32_t* out, int64_t C, int32_t mode, void* stream);
+
+/* ---- init: X.init(position, logdensity_fn) ----------------------------------------------
+ * rmhmc/rmhmc.py:96-98, lmcmc/lmc.py:98-101, lmcmonge/lmc.py:101-109.
+ * Fills logdensity, logdensity_grad (and volume_adjustment = 0 when non-NULL) from position. */
+int gb200_init(const gb200_target_desc* target, gb200_state state, int64_t C, int32_t dtype, void* stream);
+
+/* ---- step: vmap(kernel)(keys, states) ---------------------------------------------------
+ * rmhmc/rmhmc.py:131-174 (+416-462), lmcmc/lmc.py:135-180 (+451-499), lmcmonge/lmc.py:151-235 (+512-565).
+ * state_in and state_out may alias field by field (in-place) or be disjoint. */
+int gb200_step(int32_t sampler, const gb200_kernel_params* params, const gb200_target_desc* target,
+               const gb200_key_source* keys, gb200_state state_in, gb200_state state_out,
+               const gb200_info* info, const gb200_run_opts* opts, int64_t C, void* stream);
+
+int gb200_rmhmc_step(const gb200_kernel_params* params, const gb200_target_desc* target, const gb200_key_source* keys,
+                     gb200_state state_in, gb200_state state_out, const gb200_info* info, const gb200_run_opts* opts,
+                     int64_t C, void* stream);
+int gb200_lmc_step(const gb200_kernel_params* params, const gb200_target_desc* target, const gb200_key_source* keys,
+                   gb200_state state_in, gb200_state state_out, const gb200_info* info, const gb200_run_opts* opts,
+                   int64_t C, void* stream);
+int gb200_lmcmonge_step(const gb200_kernel_params* params, const gb200_target_desc* target, const gb200_key_source* keys,
+                        gb200_state state_in, gb200_state state_out, const gb200_info* info, const gb200_run_opts* opts,
+                        int64_t C, void* stream);
+
+/* ---- dual averaging: optimizers/dual_averaging.py:87-127 -------------------------------- */
+/* da[C,5] <- init(step_size0[C]) */
+int gb200_dual_averaging_init(void* da, const void* step_size0, int64_t C, int32_t dtype, void* stream);
+/* da <- update(da, target - acceptance_rate[C]) */
+int gb200_dual_averaging_update(void* da, const void* acceptance_rate, double target, double t0, double gamma,
+                                double kappa, int64_t C, int32_t dtype, void* stream);
+
+/* ---- diagnostics: geomjax/diagnostics.py:25-75 (rhat), :78-209 (ess) ---------------------
+ * samples[T, C, D] (sample_axis=0, chain_axis=1 as in examples/funnel/main.py:77-78).
+ * *_partial writes per-shard sufficient statistics (float64) that are SUM-all-reducible across
+ * ranks; *_finalize turns the (reduced) statistics into rhat[D] / ess[D] on the host. */
+/* stats[3*D+1]: sum_c mean_c, sum_c mean_c^2, sum_c var_c (ddof=1), then C */
+int gb200_rhat_partial(const void* samples, int64_t T, int64_t C, int32_t D, double* stats, int32_t dtype, void* stream);
+int gb200_rhat_finalize(const double* stats_host, int64_t T, int32_t D, double* rhat_host);
+/* acov[num_lags*D]: sum_c autocovariance_c(lag) (biased, /T) for lag < num_lags */
+int gb200_ess_partial(const void* samples, int64_t T, int64_t C, int32_t D, int32_t num_lags, double* acov,
+                      int32_t dtype, void* stream);
+/* returns per dim ess; truncated[d]=1 if Geyer's sequence was still positive at num_lags (ask for more lags) */
+int gb200_ess_finalize(const double* acov_host, const double* rhat_stats_host, int64_t T, int64_t C_total, int32_t D,
+                       int32_t num_lags, double* ess_host, uint8_t* truncated_host);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* Runs a dependent-FMA microbenchmark (iters FFMA per thread on grid x block threads) for the FP32
+ * roofline denominator; out[0] receives a checksum so the work cannot be elided. */
+int gb200_fp32_peak_kernel(float* out, int32_t grid, int32_t block, int64_t iters, void* stream);
+/* Algorithmic FP32 flop count per chain per integrator step used for roofline.achieved. */
+double gb200_flops_per_chain_step(int32_t sampler, const gb200_target_desc* target);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOMB200_H */
