@@ -9,6 +9,8 @@ from . import integrators, random, targets  # noqa: F401
 from .base import AdaptationAlgorithm, AdaptationResults, SamplingAlgorithm  # noqa: F401
 from .samplers import (LMCInfo, LMCState, Proposal, RMHMCInfo, RMHMCState, lmc, lmcmonge, rmhmc,  # noqa: F401
                        run_fused)
+from .diagnostics import effective_sample_size as ess  # noqa: F401
+from .diagnostics import potential_scale_reduction as rhat  # noqa: F401
 from .targets import TargetDescriptor, neal_funnel  # noqa: F401
 
 __version__ = "0.1.0"

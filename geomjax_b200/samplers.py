@@ -262,7 +262,7 @@ class _StepFn:
 
 def run_fused(step_fn, rng_key, state, num_samples: int, *, first: int = 0, total: Optional[int] = None,
               chain_offset: int = 0, total_chains: Optional[int] = None, return_samples: bool = False,
-              return_accept: bool = False, dual_averaging=None, da_target: float = 0.8):
+              return_accept: bool = False, dual_averaging=None, da_target: float = 0.8, inplace: bool = False):
     """Run ``num_samples`` transitions in ONE launch with in-kernel key derivation
     ``split(split(rng_key, total)[t], total_chains)[chain_offset + c]`` -- the driver loop of
     examples/funnel/main.py:7-25 (``inference_loop_multiple_chains``) without the host round trip.
@@ -289,7 +289,7 @@ def run_fused(step_fn, rng_key, state, num_samples: int, *, first: int = 0, tota
     if dual_averaging is not None:
         opts.dual_averaging = N.ptr(dual_averaging)
         opts.da_target, opts.da_t0, opts.da_gamma, opts.da_kappa = da_target, 10.0, 0.05, 0.75
-    out, _ = eng.launch(state, ks, want_info=False, opts=opts)
+    out, _ = eng.launch(state, ks, want_info=False, opts=opts, out_state=list(state) if inplace else None)
     return eng.make_state(out), samples, acc
 
 
