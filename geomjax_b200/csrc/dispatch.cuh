@@ -16,8 +16,15 @@ namespace gb {
 // in parallel; GB_MY_LAYOUTS is the subset this translation unit instantiates.
 #define GB_CAT_(a, b) a##b
 #define GB_CAT(a, b) GB_CAT_(a, b)
+// Layouts that additionally get compile-time-D ("exact", D == EPL*LPC) instantiations.
+#define GB_EXACT_1(X) X(2, 1) X(20, 1)
+#define GB_EXACT_2(X) X(10, 2)
+#define GB_EXACT_4(X) X(5, 4) X(25, 4)
+#define GB_EXACT_8(X)
+#define GB_EXACT_32(X)
 #ifdef GB_LPC
 #define GB_MY_LAYOUTS(X) GB_CAT(GB_LAYOUTS_, GB_LPC)(X)
+#define GB_MY_EXACT(X) GB_CAT(GB_EXACT_, GB_LPC)(X)
 #define GB_LPC_NAME(base) GB_CAT(GB_CAT(base, _lpc), GB_LPC)
 #endif
 

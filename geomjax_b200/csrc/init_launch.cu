@@ -10,7 +10,8 @@ __global__ void __launch_bounds__(128) init_kernel(const Target tg, gb200_state 
   long long chain = tid / LPC;
   const bool active = chain < C;
   if (!active) chain = C - 1;
-  Lay<EPL, LPC> lay{D, (int)(tid % LPC)};
+  using LAY = Lay<EPL, LPC, false>;
+  LAY lay{D, (int)(tid % LPC)};
   R q[EPL], g[EPL];
   load_vec(lay, st.position, chain, q);
   typename Target::Ctx ctx = tg.prepare(lay, q);

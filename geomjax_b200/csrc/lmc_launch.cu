@@ -1,7 +1,51 @@
+#include "lmc.cuh"
 #include "launch.h"
+
 namespace gb {
-int GB_LPC_NAME(launch_lmc)(const TransArgs&, const gb200_target_desc&, LayoutChoice, int, cudaStream_t) {
-  set_error("lmc: not built yet");
+
+template <typename R, class Target, class Metric, bool ALLOW_EXACT>
+static int launch_lmc_t(const TransArgs& a, const Target& tg, LayoutChoice lay, cudaStream_t s) {
+  int grid, block;
+  launch_shape(a.C, lay.lpc, &grid, &block);
+  if (ALLOW_EXACT) {
+#define GB_XE(E, L)                                                                   \
+  if (lay.epl == E && lay.lpc == L && a.D == E * L) {                                 \
+    lmc_kernel<R, Target, Metric, E, L, true><<<grid, block, 0, s>>>(a, tg);          \
+    GB_CHECK_LAUNCH();                                                                \
+    return GB200_OK;                                                                  \
+  }
+    GB_MY_EXACT(GB_XE)
+#undef GB_XE
+  }
+#define GB_X(E, L)                                                                    \
+  if (lay.epl == E && lay.lpc == L) {                                                 \
+    lmc_kernel<R, Target, Metric, E, L, false><<<grid, block, 0, s>>>(a, tg);         \
+    GB_CHECK_LAUNCH();                                                                \
+    return GB200_OK;                                                                  \
+  }
+  GB_MY_LAYOUTS(GB_X)
+#undef GB_X
+  set_error("lmc: no kernel for layout (%d,%d)", lay.epl, lay.lpc);
   return GB200_ERR_UNSUPPORTED;
 }
+
+int GB_LPC_NAME(launch_lmc)(const TransArgs& a, const gb200_target_desc& t, LayoutChoice lay, int dtype, cudaStream_t s) {
+  if (dtype != GB200_F32) {
+    set_error("lmc: only float32 is built in this version");
+    return GB200_ERR_UNSUPPORTED;
+  }
+  switch (t.kind) {
+    case GB200_TARGET_FUNNEL: {
+      Funnel<float> tg;
+      tg.setup(t);
+      if (t.metric == GB200_METRIC_IDENTITY)
+        return launch_lmc_t<float, Funnel<float>, IdentityMetric<float, Funnel<float>>, false>(a, tg, lay, s);
+      return launch_lmc_t<float, Funnel<float>, FunnelArrow<float>, true>(a, tg, lay, s);
+    }
+    default:
+      set_error("lmc: target kind %d has no in-kernel implementation", t.kind);
+      return GB200_ERR_UNSUPPORTED;
+  }
+}
+
 }  // namespace gb

@@ -7,68 +7,93 @@
 
 namespace gb {
 
+// Vectors a lmcmonge integrator state carries (RiemannianIntegratorState, integrators.py:26-44).
+// UNIT: inverse_mass_matrix == ones, so dl_ig == dl and ig_Hdl_ig == Hdl_ig (aliases, no storage).
+template <typename R, int EPL, bool UNIT>
+struct MongeVecs {
+  R v[EPL], dl[EPL], Hdl_ig[EPL], Hv[EPL];
+  R dl_ig_[UNIT ? 1 : EPL], ig_Hdl_ig_[UNIT ? 1 : EPL], im_[UNIT ? 1 : EPL];
+  __device__ __forceinline__ R dl_ig(int k) const { return UNIT ? dl[k] : dl_ig_[k]; }
+  __device__ __forceinline__ R ig_Hdl_ig(int k) const { return UNIT ? Hdl_ig[k] : ig_Hdl_ig_[k]; }
+  __device__ __forceinline__ R im(int k) const { return UNIT ? R(1) : im_[k]; }
+};
+
 // lmcmonge/integrators.py:158-194 (HS=omega as written / omega_fixed) and :197-230 (omegatilde).
 // All vectors are distributed; three (two for omegatilde) group reductions.
-template <typename R, int EPL, int LPC>
-__device__ __forceinline__ void monge_half_step(int HS, R a2, R (&v)[EPL], R& J, const R (&dl)[EPL], const R (&Hv)[EPL],
-                                                R L, R sL, const R (&dl_ig)[EPL], const R (&Hdl_ig)[EPL],
-                                                const R (&ig_Hdl_ig)[EPL], R eps) {
+template <typename R, int EPL, int LPC, bool UNIT>
+__device__ __forceinline__ void monge_half_step(int HS, R a2, MongeVecs<R, EPL, UNIT>& m, R& J, R L, R sL, R rs, R eps) {
   const R he = R(0.5) * eps;
+  R det1;
   if (HS == GB200_HALF_STEP_OMEGATILDE) {
-    R p[2] = {dotv<R, EPL, LPC>(Hv, dl_ig), dotv<R, EPL, LPC>(dl, v)};
-    group_sum_n<LPC>(p);
-    const R det1 = R(1) + he * a2 * p[0];
-    J -= log(fabs(det1));
-    const R c = a2 * L * p[1] + he * sL;
+    Acc4<R, EPL> s0, s1;
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) v[k] += c * dl_ig[k] - R(0.5) * a2 * eps * ig_Hdl_ig[k];
-    R r[2] = {dotv<R, EPL, LPC>(dl, v), dotv<R, EPL, LPC>(Hv, v)};
+    for (int k = 0; k < EPL; ++k) {
+      s0.fma(k, m.Hv[k], m.dl_ig(k));
+      s1.fma(k, m.dl[k], m.v[k]);
+    }
+    R p[2] = {s0.total(), s1.total()};
+    group_sum_n<LPC>(p);
+    det1 = R(1) + he * a2 * p[0];
+    const R c = a2 * L * p[1] + he * sL;
+    const R c2 = R(0.5) * a2 * eps;
+    Acc4<R, EPL> r0, r1;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+      m.v[k] += c * m.dl_ig(k) - c2 * m.ig_Hdl_ig(k);
+      r0.fma(k, m.dl[k], m.v[k]);
+      r1.fma(k, m.Hv[k], m.v[k]);
+    }
+    R r[2] = {r0.total(), r1.total()};
     group_sum_n<LPC>(r);
     const R f = a2 * (r[0] + he * r[1]) / det1;
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) v[k] -= f * dl_ig[k];
+    for (int k = 0; k < EPL; ++k) m.v[k] -= f * m.dl_ig(k);
   } else {
-    const R a2_sL = a2 / sL;
+    const R a2_sL = a2 * rs;
     R dphi_ig[EPL];
-    R p[2] = {R(0), R(0)};  // Hv.dl_ig, dphi.dl_ig
+    Acc4<R, EPL> s0, s1;  // Hv.dl_ig, dphi.dl_ig
 #pragma unroll
     for (int k = 0; k < EPL; ++k) {
-      const R dphi = a2_sL * Hdl_ig[k] - dl[k];
-      dphi_ig[k] = a2_sL * ig_Hdl_ig[k] - dl_ig[k];
-      p[0] += Hv[k] * dl_ig[k];
-      p[1] += dphi * dl_ig[k];
+      const R dphi = fma(a2_sL, m.Hdl_ig[k], -m.dl[k]);
+      dphi_ig[k] = UNIT ? dphi : fma(a2_sL, m.ig_Hdl_ig(k), -m.dl_ig(k));
+      s0.fma(k, m.Hv[k], m.dl_ig(k));
+      s1.fma(k, dphi, m.dl_ig(k));
     }
+    R p[2] = {s0.total(), s1.total()};
     group_sum_n<LPC>(p);
-    const R det1 = R(1) + he * a2 * p[0];
-    J -= log(fabs(det1));
+    det1 = R(1) + he * a2 * p[0];
     const R hs = he * sL;
     const R ab = a2 * p[1];
-    R d3 = R(0);
+    Acc4<R, EPL> s3;
 #pragma unroll
     for (int k = 0; k < EPL; ++k) {
-      v[k] -= hs * (dphi_ig[k] - ab * dl_ig[k]);
-      d3 += v[k] * Hv[k];
+      m.v[k] -= hs * fma(-ab, m.dl_ig(k), dphi_ig[k]);
+      s3.fma(k, m.v[k], m.Hv[k]);
     }
-    d3 = group_sum<LPC>(d3);
+    const R d3 = group_sum<LPC>(s3.total());
     R f = he * d3 / det1;
     if (HS == GB200_HALF_STEP_OMEGA_FIXED) f *= a2;
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) v[k] -= f * dl_ig[k];
+    for (int k = 0; k < EPL; ++k) m.v[k] -= f * m.dl_ig(k);
   }
-  R d4 = group_sum<LPC>(dotv<R, EPL, LPC>(Hdl_ig, v));
-  J += log(fabs(R(1) - he * a2 * d4));
+  Acc4<R, EPL> s4;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) s4.fma(k, m.Hdl_ig[k], m.v[k]);
+  const R d4 = group_sum<LPC>(s4.total());
+  // J += log|1 - he a2 d4| - log|det1|
+  J += fast_logabs(R(1) - he * a2 * d4) - fast_logabs(det1);
 }
 
 // lmcmonge/metrics.py:168-186 kinetic_energy (mass = 1 / inv_mass elementwise)
-template <typename R, int EPL, int LPC>
-__device__ __forceinline__ R monge_kinetic(R a2, const R (&v)[EPL], const R (&dl)[EPL], const R (&im)[EPL], R L,
-                                           R sum_log_mass) {
-  R p[2] = {R(0), R(0)};
+template <typename R, int EPL, int LPC, bool UNIT>
+__device__ __forceinline__ R monge_kinetic(R a2, const MongeVecs<R, EPL, UNIT>& m, R L, R sum_log_mass) {
+  Acc4<R, EPL> s0, s1;
 #pragma unroll
   for (int k = 0; k < EPL; ++k) {
-    p[0] += v[k] * v[k] / im[k];
-    p[1] += v[k] * dl[k];
+    s0.fma(k, m.v[k], UNIT ? m.v[k] : m.v[k] / m.im(k));
+    s1.fma(k, m.v[k], m.dl[k]);
   }
+  R p[2] = {s0.total(), s1.total()};
   group_sum_n<LPC>(p);
   return R(-0.5) * (log(L) + sum_log_mass) + R(0.5) * p[0] + R(0.5) * L * a2 * p[1] * p[1];
 }
@@ -76,50 +101,62 @@ __device__ __forceinline__ R monge_kinetic(R a2, const R (&v)[EPL], const R (&dl
 // velocity_generator, lmcmonge/metrics.py:155-166: v = chol(diag(im) - a2 u u^T) z with u = dl_ig.
 // The Cholesky factor of a diagonal-minus-rank-one matrix is L_jj = sqrt(d_j - u_j^2 s_j),
 // L_ij = u_i c_j (i > j), c_j = -u_j s_j / L_jj, s_0 = a2, s_{j+1} = s_j d_j / L_jj^2, so
-// v_i = L_ii z_i + u_i sum_{k<i} c_k z_k is an O(D) forward recurrence over the elements.
-template <typename R, int EPL, int LPC>
-__device__ __forceinline__ void monge_draw(const Lay<EPL, LPC>& lay, R a2, const R (&im)[EPL], const R (&u)[EPL],
-                                           const R (&z)[EPL], R (&v)[EPL]) {
-  R s = a2, acc = R(0);
+// v_i = L_ii z_i + u_i sum_{k<i} c_k z_k is an O(D) forward recurrence over the elements
+// (one rsqrt per element, no division).
+template <typename R, class LAY, bool UNIT>
+__device__ __forceinline__ void monge_draw(const LAY& lay, R a2, MongeVecs<R, LAY::EPL, UNIT>& m,
+                                           const R (&z)[LAY::EPL]) {
+  // The recurrence for s is a prefix sum in disguise: 1/s_{j+1} = 1/s_j - u_j^2/d_j, so
+  // t_j := 1/s_j = 1/a2 - sum_{k<j} u_k^2/d_k and acc_j = sum_{k<j} c_k z_k are two exclusive
+  // scans over the element order j = g + LPC*k; every rsqrt / rcp is then independent (ILP)
+  // instead of a D-long chain of dependent MUFU ops.  a2 == 0 gives t = inf, s = 0: v = sqrt(d) z.
+  constexpr int EPL = LAY::EPL, LPC = LAY::LPC;
+  R run = R(1) / a2;  // t at the start of the current slot row
+  R sj[EPL];
 #pragma unroll
   for (int k = 0; k < EPL; ++k) {
-#pragma unroll(LPC <= 2 ? LPC : 1)
-    for (int gg = 0; gg < LPC; ++gg) {
-      // every lane evaluates with its own slot-k data; only the owner lane gg is meaningful
-      const R ljj2 = im[k] - u[k] * u[k] * s;
-      const R ljj = sqrt(ljj2);
-      const R cz = -u[k] * s / ljj * z[k];
-      const R snext = s * im[k] / ljj2;
-      if (lay.g == gg) v[k] = lay.valid(k) ? ljj * z[k] + u[k] * acc : R(0);
-      const bool in = (gg + LPC * k) < lay.D;  // uniform across the group
-      if (LPC == 1) {
-        if (in) { acc += cz; s = snext; }
-      } else {
-        const R czb = group_bcast<LPC>(cz, gg);
-        const R snb = group_bcast<LPC>(snext, gg);
-        if (in) { acc += czb; s = snb; }
-      }
-    }
+    const R u = m.dl_ig(k);
+    const R w = lay.valid(k) ? (UNIT ? u * u : u * u / m.im(k)) : R(0);
+    R tot;
+    const R ex = group_excl_scan<LPC>(w, lay.g, tot);
+    sj[k] = fast_rcp(run - ex);
+    run -= tot;
+  }
+  R acc = R(0);
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) {
+    const R u = m.dl_ig(k), d = m.im(k);
+    const R ljj2 = fma(-u * u, sj[k], d);
+    const R r = fast_rsqrt(ljj2);
+    const R cz = lay.valid(k) ? -u * sj[k] * r * z[k] : R(0);
+    R tot;
+    const R ex = group_excl_scan<LPC>(cz, lay.g, tot);
+    m.v[k] = lay.valid(k) ? fma(ljj2 * r, z[k], u * (acc + ex)) : R(0);
+    acc += tot;
   }
 }
 
-template <typename R, class Target, int EPL, int LPC>
+template <typename R, class Target, int EPL, int LPC, bool EXACT, bool UNIT>
 __global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const Target tg) {
+  using LAY = Lay<EPL, LPC, EXACT>;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long chain = tid / LPC;
   const bool active = chain < a.C;
   if (!active) chain = a.C - 1;  // keep whole warps alive for the shuffles; writes are masked
-  Lay<EPL, LPC> lay{a.D, (int)(tid % LPC)};
+  LAY lay{a.D, (int)(tid % LPC)};
   const R a2 = (R)a.alpha2;
 
-  R im[EPL];
+  MongeVecs<R, EPL, UNIT> m;
   R slm = R(0);  // sum log(mass) = -sum log(inv_mass)
+  if (!UNIT) {
 #pragma unroll
-  for (int k = 0; k < EPL; ++k) {
-    im[k] = (a.inv_mass != nullptr && lay.valid(k)) ? ((const R*)a.inv_mass)[lay.j(k)] : R(1);
-    slm -= log(im[k]);
+    for (int k = 0; k < EPL; ++k) {
+      const R imk = (a.inv_mass != nullptr && lay.valid(k)) ? ((const R*)a.inv_mass)[lay.j(k)] : R(1);
+      m.im_[UNIT ? 0 : k] = imk;
+      slm -= log(imk);
+    }
+    slm = group_sum<LPC>(slm);
   }
-  slm = group_sum<LPC>(slm);
 
   const long long T = a.ks.keys ? 1 : a.ks.num_transitions;
   for (long long it = 0; it < T; ++it) {
@@ -138,99 +175,108 @@ __global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const 
       eps = ((const R*)a.step_size_per_chain)[chain];
     }
 
-    R q[EPL], g0[EPL];
+    R q[EPL];
     load_vec(lay, spos, chain, q);
-    load_vec(lay, sgrad, chain, g0);
+    load_vec(lay, sgrad, chain, m.dl);  // un-normalised gradient g0 for now
     const R l0 = ((const R*)slogp)[chain];
     const R J0 = ((const R*)svol)[chain];
 
     // ---- prologue: lmcmonge/lmc.py:177-208
     R L;
     {
-      R s = R(0);
+      Acc4<R, EPL> s;
 #pragma unroll
-      for (int k = 0; k < EPL; ++k) s += im[k] * g0[k] * g0[k];
-      L = R(1) + a2 * group_sum<LPC>(s);  // normalizing_constant, metrics.py:193-197
+      for (int k = 0; k < EPL; ++k) s.fma(k, m.im(k) * m.dl[k], m.dl[k]);
+      L = R(1) + a2 * group_sum<LPC>(s.total());  // normalizing_constant, metrics.py:193-197
     }
-    R sL = sqrt(L);
-    R rs = R(1) / sL;
-    const R sL0 = sL, rs0 = rs;
-    R dl[EPL], dl_ig[EPL], Hdl_ig[EPL], ig_Hdl_ig[EPL], Hv[EPL], v[EPL];
+    R rs = fast_rsqrt(L);
+    R sL = L * rs;
+    const R sL0 = sL;
 #pragma unroll
     for (int k = 0; k < EPL; ++k) {
-      dl[k] = g0[k] * rs;
-      dl_ig[k] = im[k] * dl[k];
+      m.dl[k] *= rs;
+      if (!UNIT) m.dl_ig_[UNIT ? 0 : k] = m.im(k) * m.dl[k];
     }
     U2 key = transition_key(a, chain, t);
     U2 k_v, k_a;
     split2(a.mode, key, k_v, k_a);
-    R z[EPL];
-    draw_noise<R>(a, lay, k_v, chain, z);
-    monge_draw(lay, a2, im, dl_ig, z, v);
-    if (active) {
-      store_vec(lay, a.info.noise, chain, z);
-      store_vec(lay, a.info.momentum, chain, v);  // LMCInfo.velocity = the initial draw
+    {
+      R z[EPL];
+      draw_noise<R>(a, lay, k_v, chain, z);
+      monge_draw<R, LAY, UNIT>(lay, a2, m, z);
+      if (active) store_vec(lay, a.info.noise, chain, z);
     }
+    if (active) store_vec(lay, a.info.momentum, chain, m.v);  // LMCInfo.velocity = the initial draw
     typename Target::Ctx ctx = tg.prepare(lay, q);
-    tg.hvp2(lay, ctx, q, dl_ig, v, rs, Hdl_ig, Hv);
+    {
+      R u[EPL];
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) ig_Hdl_ig[k] = im[k] * Hdl_ig[k];
+      for (int k = 0; k < EPL; ++k) u[k] = m.dl_ig(k);
+      tg.hvp2(lay, ctx, q, u, m.v, rs, m.Hdl_ig, m.Hv);
+    }
+    if (!UNIT) {
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) m.ig_Hdl_ig_[UNIT ? 0 : k] = m.im(k) * m.Hdl_ig[k];
+    }
 
     R J = J0;
-    const R H0 = -l0 + monge_kinetic<R, EPL, LPC>(a2, v, dl, im, L, slm) - J0;  // lmcmonge_energy
+    const R H0 = -l0 + monge_kinetic<R, EPL, LPC, UNIT>(a2, m, L, slm) - J0;  // lmcmonge_energy
     R lp = l0;
 
     // ---- L integrator steps: lmcmonge/integrators.py:63-153
     for (int s = 0; s < a.num_steps; ++s) {
-      monge_half_step<R, EPL, LPC>(a.half_step, a2, v, J, dl, Hv, L, sL, dl_ig, Hdl_ig, ig_Hdl_ig, eps);
+      monge_half_step<R, EPL, LPC, UNIT>(a.half_step, a2, m, J, L, sL, rs, eps);
 #pragma unroll
-      for (int k = 0; k < EPL; ++k) q[k] += eps * v[k];
+      for (int k = 0; k < EPL; ++k) q[k] = fma(eps, m.v[k], q[k]);
       ctx = tg.prepare(lay, q);
       lp = tg.logp(ctx);
-      tg.grad(lay, ctx, q, dl);  // un-normalised gradient for now
+      tg.grad(lay, ctx, q, m.dl);  // un-normalised gradient for now
       {
-        R sg = R(0);
+        Acc4<R, EPL> sg;
 #pragma unroll
-        for (int k = 0; k < EPL; ++k) sg += im[k] * dl[k] * dl[k];
-        L = R(1) + a2 * group_sum<LPC>(sg);
+        for (int k = 0; k < EPL; ++k) sg.fma(k, m.im(k) * m.dl[k], m.dl[k]);
+        L = R(1) + a2 * group_sum<LPC>(sg.total());
       }
-      sL = sqrt(L);
-      rs = R(1) / sL;
+      rs = fast_rsqrt(L);
+      sL = L * rs;
+      {
+        R u[EPL];
 #pragma unroll
-      for (int k = 0; k < EPL; ++k) {
-        dl[k] *= rs;
-        dl_ig[k] = im[k] * dl[k];
+        for (int k = 0; k < EPL; ++k) {
+          m.dl[k] *= rs;
+          if (!UNIT) m.dl_ig_[UNIT ? 0 : k] = m.im(k) * m.dl[k];
+          u[k] = m.dl_ig(k);
+        }
+        tg.hvp2(lay, ctx, q, u, m.v, rs, m.Hdl_ig, m.Hv);
       }
-      tg.hvp2(lay, ctx, q, dl_ig, v, rs, Hdl_ig, Hv);
+      if (!UNIT) {
 #pragma unroll
-      for (int k = 0; k < EPL; ++k) ig_Hdl_ig[k] = im[k] * Hdl_ig[k];
-      monge_half_step<R, EPL, LPC>(a.half_step, a2, v, J, dl, Hv, L, sL, dl_ig, Hdl_ig, ig_Hdl_ig, eps);
-      if (s + 1 < a.num_steps) tg.hvp(lay, ctx, q, v, rs, Hv);  // :132-134 (only feeds the next step)
+        for (int k = 0; k < EPL; ++k) m.ig_Hdl_ig_[UNIT ? 0 : k] = m.im(k) * m.Hdl_ig[k];
+      }
+      monge_half_step<R, EPL, LPC, UNIT>(a.half_step, a2, m, J, L, sL, rs, eps);
+      if (s + 1 < a.num_steps) tg.hvp(lay, ctx, q, m.v, rs, m.Hv);  // :132-134 (only feeds the next step)
     }
 
     // ---- flip, energy, accept: lmcmonge/lmc.py:512-534
     // energy is even in v, so evaluate on v and store -v
-    const R H1 = -lp + monge_kinetic<R, EPL, LPC>(a2, v, dl, im, L, slm) - J;
+    const R H1 = -lp + monge_kinetic<R, EPL, LPC, UNIT>(a2, m, L, slm) - J;
     MH<R> mh = metropolis<R>(a, k_a, chain, H0, H1);
 
     if (a.info.proposal_momentum != nullptr) {
       // metric_vector_product with the un-normalised gradient g = dl * sL (integrators.py:136-138)
-      R d = R(0);
-#pragma unroll
-      for (int k = 0; k < EPL; ++k) d += v[k] * dl[k];
-      d = group_sum<LPC>(d) * sL;
+      R d = group_sum<LPC>(dotv<R, EPL>(m.v, m.dl)) * sL;
       const R c = a2 * L * d * sL;
       R pm[EPL];
 #pragma unroll
-      for (int k = 0; k < EPL; ++k) pm[k] = v[k] / im[k] + c * dl[k];
+      for (int k = 0; k < EPL; ++k) pm[k] = m.v[k] / m.im(k) + c * m.dl[k];
       if (active) store_vec(lay, a.info.proposal_momentum, chain, pm, R(-1));
     }
     R gp[EPL];
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) gp[k] = dl[k] * sL;  // lmc.py:226-233
+    for (int k = 0; k < EPL; ++k) gp[k] = m.dl[k] * sL;  // lmc.py:226-233
     if (active) {
       store_vec(lay, a.info.proposal_position, chain, q);
-      store_vec(lay, a.info.proposal_velocity, chain, v, R(-1));
+      store_vec(lay, a.info.proposal_velocity, chain, m.v, R(-1));
       store_vec(lay, a.info.proposal_logdensity_grad, chain, gp);
       if (lay.g == 0) {
         store_scalar<R>(a.info.acceptance_rate, chain, mh.p_accept);
@@ -247,8 +293,10 @@ __global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const 
     if (!mh.accept) {
       // rejected: keep the input state; the returned gradient is dl0 * sqrt(L0) (lmc.py:226-233)
       load_vec(lay, spos, chain, q);
+      load_vec(lay, sgrad, chain, gp);
+      const R rs0 = R(1) / sL0;
 #pragma unroll
-      for (int k = 0; k < EPL; ++k) gp[k] = (g0[k] * rs0) * sL0;
+      for (int k = 0; k < EPL; ++k) gp[k] = (gp[k] * rs0) * sL0;
       lp = l0;
       J = J0;
     }

@@ -7,11 +7,21 @@ template <typename R, class Target>
 static int launch_lmcmonge_t(const TransArgs& a, const Target& tg, LayoutChoice lay, cudaStream_t s) {
   int grid, block;
   launch_shape(a.C, lay.lpc, &grid, &block);
-#define GB_X(E, L)                                                        \
-  if (lay.epl == E && lay.lpc == L) {                                     \
-    lmcmonge_kernel<R, Target, E, L><<<grid, block, 0, s>>>(a, tg);       \
-    GB_CHECK_LAUNCH();                                                    \
-    return GB200_OK;                                                      \
+  const bool unit = a.inv_mass == nullptr;
+#define GB_XE(E, L)                                                                         \
+  if (lay.epl == E && lay.lpc == L && a.D == E * L) {                                       \
+    if (unit) lmcmonge_kernel<R, Target, E, L, true, true><<<grid, block, 0, s>>>(a, tg);   \
+    else lmcmonge_kernel<R, Target, E, L, true, false><<<grid, block, 0, s>>>(a, tg);       \
+    GB_CHECK_LAUNCH();                                                                      \
+    return GB200_OK;                                                                        \
+  }
+  GB_MY_EXACT(GB_XE)
+#undef GB_XE
+#define GB_X(E, L)                                                                    \
+  if (lay.epl == E && lay.lpc == L) {                                                 \
+    lmcmonge_kernel<R, Target, E, L, false, false><<<grid, block, 0, s>>>(a, tg);     \
+    GB_CHECK_LAUNCH();                                                                \
+    return GB200_OK;                                                                  \
   }
   GB_MY_LAYOUTS(GB_X)
 #undef GB_X

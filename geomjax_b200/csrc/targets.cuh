@@ -6,14 +6,41 @@
 
 namespace gb {
 
-template <int EPL, int LPC>
+// EXACT: D == EPL * LPC is known at compile time, so every validity / "is this the last
+// element" predicate folds to a constant (no ISETP/FSEL per slot).
+template <int EPL_, int LPC_, bool EXACT_>
 struct Lay {
-  int D;  // runtime dimension, D <= EPL * LPC
-  int g;  // lane within the group
+  static constexpr int EPL = EPL_, LPC = LPC_;
+  static constexpr bool EXACT = EXACT_;
+  int D_;  // runtime dimension, D <= EPL * LPC
+  int g;   // lane within the group
+  __device__ __forceinline__ int D() const { return EXACT ? EPL * LPC : D_; }
   __device__ __forceinline__ int j(int k) const { return g + LPC * k; }
-  __device__ __forceinline__ bool valid(int k) const { return j(k) < D; }
-  __device__ __forceinline__ bool last(int k) const { return j(k) == D - 1; }
+  __device__ __forceinline__ bool valid(int k) const { return EXACT ? true : (j(k) < D_); }
+  __device__ __forceinline__ bool last(int k) const {
+    if (EXACT) return (k == EPL - 1) && (LPC == 1 || g == LPC - 1);
+    return j(k) == D_ - 1;
+  }
 };
+
+// 4-way split accumulation: a serial chain of EPL dependent FMAs would expose 4*EPL cycles of
+// latency per dot product; four partial sums cut the chain to EPL/4 + 2.
+template <typename R, int EPL>
+struct Acc4 {
+  R a[4];
+  __device__ __forceinline__ Acc4() { a[0] = a[1] = a[2] = a[3] = R(0); }
+  __device__ __forceinline__ void fma(int k, R x, R y) { a[k & 3] = ::fma(x, y, a[k & 3]); }
+  __device__ __forceinline__ void add(int k, R x) { a[k & 3] += x; }
+  __device__ __forceinline__ R total() const { return (a[0] + a[1]) + (a[2] + a[3]); }
+};
+
+template <typename R, int EPL>
+__device__ __forceinline__ R dotv(const R (&a)[EPL], const R (&b)[EPL]) {
+  Acc4<R, EPL> s;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) s.fma(k, a[k], b[k]);
+  return s.total();
+}
 
 // Neal's funnel: examples/funnel/main.py:28-54.
 //   l(theta) = N(v; 0, sigma) + sum_{i<D-1} N(x_i; 0, exp(v/2)),  v = theta[D-1]
@@ -22,6 +49,7 @@ struct Lay {
 template <typename R>
 struct Funnel {
   R inv_s2;   // 1 / sigma^2
+  R sigma;
   R c0;       // -0.5 log(2 pi sigma^2) - (D-1)/2 log(2 pi)
   R hdm1;     // (D-1)/2
   struct Ctx { R v, e, S; };
@@ -29,20 +57,23 @@ struct Funnel {
   __host__ void setup(const gb200_target_desc& t) {
     const double s = t.params[0];
     inv_s2 = (R)(1.0 / (s * s));
+    sigma = (R)s;
     c0 = (R)(-0.5 * log(2.0 * M_PI * s * s) - 0.5 * (t.D - 1) * log(2.0 * M_PI));
     hdm1 = (R)(0.5 * (t.D - 1));
   }
 
-  template <int EPL, int LPC>
-  __device__ __forceinline__ Ctx prepare(const Lay<EPL, LPC>& lay, const R (&q)[EPL]) const {
-    R p[2] = {R(0), R(0)};
+  template <class LAY>
+  __device__ __forceinline__ Ctx prepare(const LAY& lay, const R (&q)[LAY::EPL]) const {
+    Acc4<R, LAY::EPL> s;
+    R vl = R(0);
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) {
+    for (int k = 0; k < LAY::EPL; ++k) {
       const bool l = lay.last(k);
-      p[0] += l ? R(0) : q[k] * q[k];
-      p[1] += l ? q[k] : R(0);
+      s.fma(k, l ? R(0) : q[k], q[k]);
+      vl += l ? q[k] : R(0);
     }
-    group_sum_n<LPC>(p);
+    R p[2] = {s.total(), vl};
+    group_sum_n<LAY::LPC>(p);
     Ctx c;
     c.S = p[0];
     c.v = p[1];
@@ -54,57 +85,64 @@ struct Funnel {
     return c0 - R(0.5) * c.v * c.v * inv_s2 - hdm1 * c.v - R(0.5) * c.e * c.S;
   }
 
-  template <int EPL, int LPC>
-  __device__ __forceinline__ void grad(const Lay<EPL, LPC>& lay, const Ctx& c, const R (&q)[EPL],
-                                       R (&g)[EPL]) const {
+  template <class LAY>
+  __device__ __forceinline__ void grad(const LAY& lay, const Ctx& c, const R (&q)[LAY::EPL],
+                                       R (&g)[LAY::EPL]) const {
     const R gv = -c.v * inv_s2 - hdm1 + R(0.5) * c.e * c.S;
+    const R me = -c.e;
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) g[k] = lay.last(k) ? gv : -q[k] * c.e;
+    for (int k = 0; k < LAY::EPL; ++k) g[k] = lay.last(k) ? gv : q[k] * me;
   }
 
   // Two Hessian-vector products with one reduction round: o1 = H u1 * s, o2 = H u2 * s.
-  template <int EPL, int LPC>
-  __device__ __forceinline__ void hvp2(const Lay<EPL, LPC>& lay, const Ctx& c, const R (&q)[EPL],
-                                       const R (&u1)[EPL], const R (&u2)[EPL], R s,
-                                       R (&o1)[EPL], R (&o2)[EPL]) const {
-    R p[4] = {R(0), R(0), R(0), R(0)};  // x.u1, u1_last, x.u2, u2_last
+  template <class LAY>
+  __device__ __forceinline__ void hvp2(const LAY& lay, const Ctx& c, const R (&q)[LAY::EPL],
+                                       const R (&u1)[LAY::EPL], const R (&u2)[LAY::EPL], R s,
+                                       R (&o1)[LAY::EPL], R (&o2)[LAY::EPL]) const {
+    Acc4<R, LAY::EPL> d1, d2;
+    R l1v = R(0), l2v = R(0);
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) {
+    for (int k = 0; k < LAY::EPL; ++k) {
       const bool l = lay.last(k);
-      p[0] += l ? R(0) : q[k] * u1[k];
-      p[1] += l ? u1[k] : R(0);
-      p[2] += l ? R(0) : q[k] * u2[k];
-      p[3] += l ? u2[k] : R(0);
+      d1.fma(k, l ? R(0) : q[k], u1[k]);
+      d2.fma(k, l ? R(0) : q[k], u2[k]);
+      l1v += l ? u1[k] : R(0);
+      l2v += l ? u2[k] : R(0);
     }
-    group_sum_n<LPC>(p);
+    R p[4] = {d1.total(), l1v, d2.total(), l2v};  // x.u1, u1_last, x.u2, u2_last
+    group_sum_n<LAY::LPC>(p);
     const R es = c.e * s;
     const R hvv = -(inv_s2 + R(0.5) * c.e * c.S) * s;
     const R l1 = es * p[0] + hvv * p[1];
     const R l2 = es * p[2] + hvv * p[3];
+    const R a1 = es * p[1], a2 = es * p[3];
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) {
+    for (int k = 0; k < LAY::EPL; ++k) {
       const bool l = lay.last(k);
-      o1[k] = l ? l1 : es * (q[k] * p[1] - u1[k]);
-      o2[k] = l ? l2 : es * (q[k] * p[3] - u2[k]);
+      o1[k] = l ? l1 : ::fma(q[k], a1, -es * u1[k]);
+      o2[k] = l ? l2 : ::fma(q[k], a2, -es * u2[k]);
     }
   }
 
-  template <int EPL, int LPC>
-  __device__ __forceinline__ void hvp(const Lay<EPL, LPC>& lay, const Ctx& c, const R (&q)[EPL],
-                                      const R (&u)[EPL], R s, R (&o)[EPL]) const {
-    R p[2] = {R(0), R(0)};
+  template <class LAY>
+  __device__ __forceinline__ void hvp(const LAY& lay, const Ctx& c, const R (&q)[LAY::EPL],
+                                      const R (&u)[LAY::EPL], R s, R (&o)[LAY::EPL]) const {
+    Acc4<R, LAY::EPL> d;
+    R lv = R(0);
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) {
+    for (int k = 0; k < LAY::EPL; ++k) {
       const bool l = lay.last(k);
-      p[0] += l ? R(0) : q[k] * u[k];
-      p[1] += l ? u[k] : R(0);
+      d.fma(k, l ? R(0) : q[k], u[k]);
+      lv += l ? u[k] : R(0);
     }
-    group_sum_n<LPC>(p);
+    R p[2] = {d.total(), lv};
+    group_sum_n<LAY::LPC>(p);
     const R es = c.e * s;
     const R hvv = -(inv_s2 + R(0.5) * c.e * c.S) * s;
-    const R lv = es * p[0] + hvv * p[1];
+    const R ll = es * p[0] + hvv * p[1];
+    const R a1 = es * p[1];
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) o[k] = lay.last(k) ? lv : es * (q[k] * p[1] - u[k]);
+    for (int k = 0; k < LAY::EPL; ++k) o[k] = lay.last(k) ? ll : ::fma(q[k], a1, -es * u[k]);
   }
 };
 

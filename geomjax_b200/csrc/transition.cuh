@@ -35,17 +35,33 @@ __device__ __forceinline__ U2 transition_key(const TransArgs& a, long long chain
   }
   U2 root{a.ks.root_key[0], a.ks.root_key[1]};
   return chain_key(a.mode, root, (uint32_t)a.ks.total_transitions, (uint32_t)t,
-                         (uint32_t)a.ks.total_chains, (uint32_t)(a.ks.chain_offset + chain));
+                   (uint32_t)a.ks.total_chains, (uint32_t)(a.ks.chain_offset + chain));
 }
 
 // z = jax.random.normal(key, (D,)) distributed over the lane group (util.py:81-82).
-template <typename R, int EPL, int LPC>
-__device__ __forceinline__ void draw_noise(const TransArgs& a, const Lay<EPL, LPC>& lay, U2 key,
-                                           long long chain, R (&z)[EPL]) {
+// Legacy threefry hashes the counters pairwise (i, i + D/2): when the layout is exact, D is
+// even and both halves of a pair live in the same lane, one block yields two normals.
+template <typename R, class LAY>
+__device__ __forceinline__ void draw_noise(const TransArgs& a, const LAY& lay, U2 key, long long chain,
+                                           R (&z)[LAY::EPL]) {
+  constexpr int EPL = LAY::EPL, LPC = LAY::LPC;
   if (a.opts.noise_override != nullptr) {
     const R* zo = (const R*)a.opts.noise_override + chain * a.D;
 #pragma unroll
     for (int k = 0; k < EPL; ++k) z[k] = lay.valid(k) ? zo[lay.j(k)] : R(0);
+    return;
+  }
+  constexpr int DS = EPL * LPC;
+  constexpr bool PAIRED = LAY::EXACT && (DS % 2 == 0) && ((DS / 2) % LPC == 0);
+  if (PAIRED && a.mode == GB200_THREEFRY_LEGACY) {
+    constexpr int HK = EPL / 2;  // slots per half
+#pragma unroll
+    for (int k = 0; k < HK; ++k) {
+      const uint32_t j = (uint32_t)lay.j(k);
+      U2 o = threefry2x32(key.x, key.y, j, j + (uint32_t)(DS / 2));
+      z[k] = (R)bits_to_normal(o.x);
+      z[k + HK] = (R)bits_to_normal(o.y);
+    }
     return;
   }
 #pragma unroll
@@ -89,18 +105,19 @@ __device__ __forceinline__ void dual_averaging_update(R* da, R accept_rate, R ta
   da[3] = avg_err;
 }
 
-template <typename R, int EPL, int LPC>
-__device__ __forceinline__ void load_vec(const Lay<EPL, LPC>& lay, const void* base, long long chain, R (&v)[EPL]) {
-  const R* p = (const R*)base + chain * lay.D;
+template <typename R, class LAY>
+__device__ __forceinline__ void load_vec(const LAY& lay, const void* base, long long chain, R (&v)[LAY::EPL]) {
+  const R* p = (const R*)base + chain * lay.D();
 #pragma unroll
-  for (int k = 0; k < EPL; ++k) v[k] = lay.valid(k) ? p[lay.j(k)] : R(0);
+  for (int k = 0; k < LAY::EPL; ++k) v[k] = lay.valid(k) ? p[lay.j(k)] : R(0);
 }
-template <typename R, int EPL, int LPC>
-__device__ __forceinline__ void store_vec(const Lay<EPL, LPC>& lay, void* base, long long chain, const R (&v)[EPL], R sign = R(1)) {
+template <typename R, class LAY>
+__device__ __forceinline__ void store_vec(const LAY& lay, void* base, long long chain, const R (&v)[LAY::EPL],
+                                          R sign = R(1)) {
   if (base == nullptr) return;
-  R* p = (R*)base + chain * lay.D;
+  R* p = (R*)base + chain * lay.D();
 #pragma unroll
-  for (int k = 0; k < EPL; ++k)
+  for (int k = 0; k < LAY::EPL; ++k)
     if (lay.valid(k)) p[lay.j(k)] = sign * v[k];
 }
 template <typename R>
@@ -108,12 +125,14 @@ __device__ __forceinline__ void store_scalar(void* base, long long chain, R v) {
   if (base != nullptr) ((R*)base)[chain] = v;
 }
 
-template <typename R, int EPL, int LPC>
-__device__ __forceinline__ R dotv(const R (&a)[EPL], const R (&b)[EPL]) {
-  R s = R(0);
-#pragma unroll
-  for (int k = 0; k < EPL; ++k) s += a[k] * b[k];
-  return s;
-}
+// fast scalar helpers (float: MUFU-based intrinsics, <= 2 ulp; double: exact library calls)
+__device__ __forceinline__ float fast_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double fast_rsqrt(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
+// log|x| for volume adjustments: |abs error| <= 2^-21.4 for x in [0.5, 2] (CUDA __logf), which is
+// below the float32 resolution of the O(10) energies it is added to.
+__device__ __forceinline__ float fast_logabs(float x) { return __logf(fabsf(x)); }
+__device__ __forceinline__ double fast_logabs(double x) { return log(fabs(x)); }
 
 }  // namespace gb

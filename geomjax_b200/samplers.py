@@ -135,6 +135,9 @@ class _Engine:
         self.step_size = step_size
         self.L = int(num_integration_steps)
         self.divergence_threshold = float(divergence_threshold)
+        if isinstance(inverse_mass_matrix, (torch.Tensor, np.ndarray)) and inverse_mass_matrix.ndim == 1 \
+                and bool((torch.as_tensor(inverse_mass_matrix) == 1).all()):
+            inverse_mass_matrix = None  # ones: the C ABI takes NULL and runs the unit-mass kernels
         self.inverse_mass_matrix = inverse_mass_matrix
         self.alpha2 = float(alpha2)
         self.half_step = N.HALF_STEP[half_step]

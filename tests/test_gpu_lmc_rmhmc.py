@@ -1,0 +1,173 @@
+"""Fused CUDA lmc (Lan integrator, arrow-matrix closed forms) and rmhmc (implicit midpoint)
+against the dense NumPy oracle (which follows the reference line by line)."""
+import numpy as np
+import pytest
+
+from oracle import prng as P
+from oracle import samplers as S
+from oracle import targets as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(x, dev):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def _close(got, want, rtol=1e-5, atol=1e-6, what=""):
+    """Element-wise rtol plus a NORM-WISE floor: the oracle (like the reference) pushes every vector
+    through dense float32 LAPACK (Cholesky / LU / solve), whose forward error is ~ D * eps_f32
+    relative to the vector norm, not to each element; the closed forms on the GPU are more
+    accurate than that (see test_lmc_closer_to_float64_than_the_float32_oracle)."""
+    got = got.cpu().numpy() if hasattr(got, "cpu") else np.asarray(got)
+    want = np.asarray(want)
+    floor = 3e-5 * float(np.abs(want[np.isfinite(want)]).max()) if want.ndim == 2 and want.size and want.shape[1] >= 33 else 0.0
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=max(atol, floor), err_msg=what)
+
+
+def _setup(D, C, seed=0, scale=0.5):
+    rng = np.random.default_rng(seed)
+    v = 0.7 * scale * rng.standard_normal((C, 1))
+    q = np.concatenate([np.exp(0.5 * v) * rng.standard_normal((C, D - 1)) * scale, v], axis=1).astype(np.float32)
+    keys = rng.integers(0, 2 ** 32, size=(C, 2), dtype=np.uint64).astype(np.uint32)
+    return q, keys
+
+
+CASES = [(2, 1, 128), (2, 2, 128), (5, 4, 128), (20, 1, 96), (20, 2, 96), (20, 4, 96), (33, 32, 32), (100, 4, 12), (100, 8, 12)]
+
+
+@pytest.mark.parametrize("L,rtol", [(1, 1e-5), (8, 1e-4)])
+@pytest.mark.parametrize("D,lpc,C", CASES)
+def test_lmc_vs_oracle(cuda, D, lpc, C, L, rtol):
+    import geomjax_b200 as g
+    q, keys = _setup(D, C, seed=D + 1)
+    tgt = T.NealFunnel(D)
+    eps = 0.2 / np.sqrt(D) / L ** 0.5
+    ost = S.lmc_init(q, tgt)
+    onew, oinfo = S.lmc_step(keys, ost, tgt, eps, L)
+    target = g.neal_funnel(D)
+    alg = g.lmc(target, eps, target, L, lanes_per_chain=lpc)
+    st = alg.init(_t(q, cuda))
+    new, info = alg.step(_t(keys, cuda), st)
+    with np.errstate(invalid="ignore"):
+        tame = np.isfinite(oinfo.proposal["weight"]) & (np.abs(oinfo.proposal["weight"]) < 50)
+    assert tame.mean() > 0.9 and oinfo.is_accepted.mean() > 0.3
+    tm = _t(tame, cuda)
+    ps = info.proposal.state
+    _close(info.velocity, oinfo.momentum, rtol=1e-5, atol=1e-6, what="velocity draw")
+    _close(ps.position[tm], oinfo.proposal["position"][tame], rtol=rtol, atol=1e-6, what="position")
+    _close(ps.velocity[tm], oinfo.proposal["velocity"][tame], rtol=rtol, atol=1e-5, what="velocity")
+    _close(ps.momentum[tm], oinfo.proposal["momentum"][tame], rtol=rtol, atol=1e-4, what="momentum")
+    _close(ps.logdensity[tm], oinfo.proposal["logdensity"][tame], rtol=rtol, atol=1e-4)
+    # the oracle's volume term is a sum of 4 float32 LU log-dets per step (error ~ D * eps_f32 each)
+    vol_atol = max(2e-5, 1e-6 * D * L)
+    _close(ps.volume_adjustment[tm], oinfo.proposal["volume_adjustment"][tame], rtol=rtol, atol=vol_atol, what="volume")
+    _close(info.energy[tm], oinfo.energy[tame], rtol=rtol, atol=2e-4, what="energy")
+    _close(info.acceptance_rate[tm], oinfo.acceptance_rate[tame], rtol=10 * rtol, atol=1e-3)
+    got_acc = info.is_accepted.cpu().numpy()
+    clear = np.abs(oinfo.extra["u"] - oinfo.acceptance_rate) > 4e-3
+    np.testing.assert_array_equal(got_acc[clear], oinfo.is_accepted[clear])
+    same = (got_acc == oinfo.is_accepted) & tame
+    _close(new.position[_t(same, cuda)], onew.position[same], rtol=rtol)
+    _close(new.volume_adjustment[_t(same, cuda)], onew.volume_adjustment[same], rtol=rtol, atol=vol_atol)
+
+
+@pytest.mark.parametrize("L,rtol", [(1, 2e-5), (4, 1e-4)])
+@pytest.mark.parametrize("D,lpc,C", CASES)
+def test_rmhmc_vs_oracle(cuda, D, lpc, C, L, rtol):
+    import geomjax_b200 as g
+    q, keys = _setup(D, C, seed=D + 2)
+    tgt = T.NealFunnel(D)
+    eps = 0.1 / np.sqrt(D)
+    ost = S.rmhmc_init(q, tgt)
+    onew, oinfo = S.rmhmc_step(keys, ost, tgt, eps, L)
+    target = g.neal_funnel(D)
+    alg = g.rmhmc(target, eps, target, L, lanes_per_chain=lpc)
+    st = alg.init(_t(q, cuda))
+    _close(st.logdensity_grad, ost.logdensity_grad)
+    new, info = alg.step(_t(keys, cuda), st)
+    with np.errstate(invalid="ignore"):
+        tame = np.isfinite(oinfo.proposal["weight"]) & (np.abs(oinfo.proposal["weight"]) < 50) \
+            & (oinfo.extra["fp_iters"] < 60 * L)
+    assert tame.mean() > 0.8 and oinfo.is_accepted.mean() > 0.3
+    tm = _t(tame, cuda)
+    ps = info.proposal.state
+    _close(info.momentum, oinfo.momentum, rtol=1e-5, atol=1e-6, what="momentum draw")
+    # fixed-point tolerance 1e-6 is absolute: both sides stop within ~1e-6 of the same fixed point
+    _close(ps.position[tm], oinfo.proposal["position"][tame], rtol=rtol, atol=5e-6, what="position")
+    _close(ps.momentum[tm], oinfo.proposal["momentum"][tame], rtol=rtol, atol=2e-5, what="momentum")
+    _close(ps.velocity[tm], oinfo.proposal["velocity"][tame], rtol=rtol, atol=2e-5, what="velocity")
+    _close(ps.logdensity[tm], oinfo.proposal["logdensity"][tame], rtol=rtol, atol=2e-4)
+    _close(info.energy[tm], oinfo.energy[tame], rtol=rtol, atol=3e-4, what="energy")
+    got_acc = info.is_accepted.cpu().numpy()
+    clear = np.abs(oinfo.extra["u"] - oinfo.acceptance_rate) > 4e-3
+    np.testing.assert_array_equal(got_acc[clear & tame], oinfo.is_accepted[clear & tame])
+
+
+def test_lmc_closer_to_float64_than_the_float32_oracle(cuda):
+    """D=100: |CUDA - f64 oracle| <= |f32 oracle - f64 oracle| (+ small slack) for one Lan step."""
+    import geomjax_b200 as g
+    D, C, eps = 100, 8, 0.02
+    q, keys = _setup(D, C, seed=7)
+    o32, i32 = S.lmc_step(keys, S.lmc_init(q, T.NealFunnel(D)), T.NealFunnel(D), eps, 1)
+    t64 = T.NealFunnel(D, dtype=np.float64)
+    o64, i64 = S.lmc_step(keys, S.lmc_init(q, t64), t64, eps, 1, z=i32.extra["z"], u=i32.extra["u"])
+    target = g.neal_funnel(D)
+    alg = g.lmc(target, eps, target, 1)
+    new, info = alg.step(_t(keys, cuda), alg.init(_t(q, cuda)))
+    for name, got in (("position", info.proposal.state.position), ("velocity", info.proposal.state.velocity)):
+        e_gpu = np.abs(got.cpu().numpy() - i64.proposal[name]).max()
+        e_o32 = np.abs(i32.proposal[name] - i64.proposal[name]).max()
+        assert e_gpu <= 2.0 * e_o32 + 2e-6, (name, e_gpu, e_o32)
+    e_gpu = np.abs(info.proposal.state.volume_adjustment.cpu().numpy() - i64.proposal["volume_adjustment"]).max()
+    e_o32 = np.abs(i32.proposal["volume_adjustment"] - i64.proposal["volume_adjustment"]).max()
+    assert e_gpu <= 2.0 * e_o32 + 2e-6, ("volume", e_gpu, e_o32)
+    e_gpu = np.abs(info.energy.cpu().numpy() - i64.energy).max()
+    e_o32 = np.abs(i32.energy - i64.energy).max()
+    assert e_gpu <= 2.0 * e_o32 + 1e-4, (e_gpu, e_o32)
+
+
+def test_reference_test_equivalences_on_gpu(cuda):
+    """tests/test_samplers.py:21-57 on the CUDA path: G = I => rmhmc ~ lmc (~ hmc) at rtol 1e-4,
+    and the SURVEY Appendix A.2 candidate values for key 42."""
+    import geomjax_b200 as g
+    target = g.neal_funnel(2)
+    key = _t(P.key(42)[None], cuda)
+    z = _t(np.zeros((1, 2), np.float32), cuda)
+    s1, _ = g.rmhmc(target, 1e-2, "identity", 10).step(key, g.rmhmc.init(z, target))
+    s3, _ = g.lmc(target, 1e-2, "identity", 10).step(key, g.lmc.init(z, target))
+    np.testing.assert_allclose(s1.position.cpu().numpy(), s3.position.cpu().numpy(), rtol=1e-4)
+    _close(s3.position, np.array([[0.06480624, -0.06973797]], np.float32), rtol=1e-5)
+    _close(s1.position, np.array([[0.064804554, -0.06973776]], np.float32), rtol=2e-5)
+    # funnel metric, same key: lmc and rmhmc follow the same dynamics
+    s4, i4 = g.rmhmc(target, 1e-2, target, 10).step(key, g.rmhmc.init(z, target))
+    s5, i5 = g.lmc(target, 1e-2, target, 10).step(key, g.lmc.init(z, target))
+    _close(i4.proposal.state.position, np.array([[0.058600806, -0.20142354]], np.float32), rtol=2e-5)
+    _close(i5.proposal.state.position, np.array([[0.058600716, -0.20142427]], np.float32), rtol=2e-5)
+    _close(i5.proposal.state.volume_adjustment, np.array([-0.20142305], np.float32), rtol=1e-4)
+    _close(i4.momentum, np.array([[0.6491706, -0.22417447]], np.float32), rtol=1e-6)
+    _close(i5.velocity, np.array([[0.6491706, -2.01757]], np.float32), rtol=1e-6)
+
+
+def test_shipped_example_first_transition(cuda):
+    """examples/funnel/main.py as shipped (lmc, funnel metric, eps=0.1, L=8, ones(2), PRNGKey(0), 8 chains)."""
+    import torch
+    import geomjax_b200 as g
+    target = g.neal_funnel(2)
+    alg = g.lmc(target, 0.1, target.fisher_metric_fn, 8)
+    st0 = alg.init(torch.ones((8, 2), device=cuda))
+    root = g.random.PRNGKey(0)
+    st, samples, acc = g.run_fused(alg.step, root, st0, 3, total=1000, return_samples=True)
+    keys = g.random.chain_keys(root, 0, 1000, 8)
+    st1, info = alg.step(keys, st0)
+    assert bool((samples[0] == st1.position).all())
+    _close(info.velocity[0], np.array([-0.022572383, -0.44815361], np.float32), rtol=2e-6)
+    _close(info.proposal.state.position[0], np.array([0.61434513, 0.37447447], np.float32), rtol=2e-5)
+    _close(info.proposal.state.volume_adjustment[0], np.float32(-0.62510157), rtol=1e-4)
+    assert bool(info.is_accepted[0])
+    tgt = T.NealFunnel(2)
+    ost = S.lmc_init(np.ones((8, 2), np.float32), tgt)
+    onew, oinfo = S.lmc_step(S.chain_keys(P.key(0), 1000, 0, 8), ost, tgt, 0.1, 8)
+    _close(st1.position, onew.position, rtol=1e-4)
+    np.testing.assert_array_equal(info.is_accepted.cpu().numpy(), oinfo.is_accepted)
