@@ -6,6 +6,7 @@ Drop-in for the reference's hot path only (geomjax/__init__.py:17-25 names):
 hand-written CUDA for sm_100a behind the C ABI of ``include/geomb200.h``.
 """
 from . import integrators, random, targets  # noqa: F401
+from .adaptation import dual_averaging, step_size_adaptation, window_adaptation  # noqa: F401
 from .base import AdaptationAlgorithm, AdaptationResults, SamplingAlgorithm  # noqa: F401
 from .samplers import (LMCInfo, LMCState, Proposal, RMHMCInfo, RMHMCState, lmc, lmcmonge, rmhmc,  # noqa: F401
                        run_fused)

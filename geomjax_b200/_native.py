@@ -36,7 +36,8 @@ class KernelParams(C.Structure):
                 ("divergence_threshold", C.c_double), ("fp_convergence_tol", C.c_double),
                 ("fp_divergence_tol", C.c_double), ("fp_max_iters", C.c_int32), ("half_step", C.c_int32),
                 ("alpha2", C.c_double), ("inverse_mass_matrix", vp),
-                ("dtype", C.c_int32), ("lanes_per_chain", C.c_int32)]
+                ("dtype", C.c_int32), ("lanes_per_chain", C.c_int32),
+                ("inverse_mass_per_chain", C.c_int32), ("reserved", C.c_int32)]
 
 
 class State(C.Structure):

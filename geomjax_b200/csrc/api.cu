@@ -187,6 +187,7 @@ int gb200_step(int32_t sampler, const gb200_kernel_params* p, const gb200_target
   a.step_size = p->step_size;
   a.step_size_per_chain = p->step_size_per_chain;
   a.inv_mass = p->inverse_mass_matrix;
+  a.inv_mass_stride = p->inverse_mass_per_chain ? target->D : 0;
   a.alpha2 = p->alpha2;
   a.divergence_threshold = p->divergence_threshold;
   a.fp_tol = p->fp_convergence_tol;

@@ -230,7 +230,7 @@ double gb200_flops_per_chain_step(int32_t sampler, const gb200_target_desc* t) {
   if (t->kind == GB200_TARGET_FUNNEL) {
     switch (sampler) {
       case GB200_LMCMONGE: return 59.0 * D + 60.0;
-      case GB200_LMC: return 92.0 * D + 140.0;
+      case GB200_LMC: return 25.0 * D + 140.0;
       case GB200_RMHMC: return 0.0;  // depends on fixed-point iterations; reported per f-eval separately
     }
   }

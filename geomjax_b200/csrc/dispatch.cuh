@@ -41,8 +41,9 @@ inline bool choose_layout(int D, int lpc_req, long long C, LayoutChoice* out) {
   if (lpc_req == 0) {
     // heuristic: keep <= ~24 elements per lane (register arrays) and prefer few lanes per
     // chain (no shuffle / redundant scalar work) when there are enough chains to fill the GPU.
+    // measured on B200 (tools/sweep.py, funnel D=20, 65,536 chains): 2 lanes/chain beats 1 and 4
+    // for lmcmonge (46 vs 56 vs 55 us/transition) and ties with 1 for lmc.
     if (D <= 12) lpc_req = 1;
-    else if (D <= 20) lpc_req = (C >= 32768) ? 1 : 2;
     else if (D <= 32) lpc_req = 2;
     else if (D <= 100) lpc_req = 4;
     else if (D <= 256) lpc_req = 8;

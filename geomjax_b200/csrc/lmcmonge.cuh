@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const 
   if (!UNIT) {
 #pragma unroll
     for (int k = 0; k < EPL; ++k) {
-      const R imk = (a.inv_mass != nullptr && lay.valid(k)) ? ((const R*)a.inv_mass)[lay.j(k)] : R(1);
+      const R imk = (a.inv_mass != nullptr && lay.valid(k))
+                        ? ((const R*)a.inv_mass)[chain * a.inv_mass_stride + lay.j(k)] : R(1);
       m.im_[UNIT ? 0 : k] = imk;
       slm -= log(imk);
     }

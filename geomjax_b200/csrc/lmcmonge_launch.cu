@@ -10,8 +10,8 @@ static int launch_lmcmonge_t(const TransArgs& a, const Target& tg, LayoutChoice 
   const bool unit = a.inv_mass == nullptr;
 #define GB_XE(E, L)                                                                         \
   if (lay.epl == E && lay.lpc == L && a.D == E * L) {                                       \
-    if (unit) lmcmonge_kernel<R, Target, E, L, true, true><<<grid, block, 0, s>>>(a, tg);   \
-    else lmcmonge_kernel<R, Target, E, L, true, false><<<grid, block, 0, s>>>(a, tg);       \
+    if (unit) lmcmonge_kernel<R, Target, E, L, true, true><<<grid, block, (size_t)block * lay.epl * sizeof(R), s>>>(a, tg);   \
+    else lmcmonge_kernel<R, Target, E, L, true, false><<<grid, block, (size_t)block * lay.epl * sizeof(R), s>>>(a, tg);       \
     GB_CHECK_LAUNCH();                                                                      \
     return GB200_OK;                                                                        \
   }
@@ -19,7 +19,7 @@ static int launch_lmcmonge_t(const TransArgs& a, const Target& tg, LayoutChoice 
 #undef GB_XE
 #define GB_X(E, L)                                                                    \
   if (lay.epl == E && lay.lpc == L) {                                                 \
-    lmcmonge_kernel<R, Target, E, L, false, false><<<grid, block, 0, s>>>(a, tg);     \
+    lmcmonge_kernel<R, Target, E, L, false, false><<<grid, block, (size_t)block * lay.epl * sizeof(R), s>>>(a, tg);     \
     GB_CHECK_LAUNCH();                                                                \
     return GB200_OK;                                                                  \
   }

@@ -7,10 +7,10 @@ template <typename R, class Target, class Metric, bool ALLOW_EXACT>
 static int launch_rmhmc_t(const TransArgs& a, const Target& tg, LayoutChoice lay, cudaStream_t s) {
   int grid, block;
   launch_shape(a.C, lay.lpc, &grid, &block);
-  if (ALLOW_EXACT) {
+  if constexpr (ALLOW_EXACT) {
 #define GB_XE(E, L)                                                                   \
   if (lay.epl == E && lay.lpc == L && a.D == E * L) {                                 \
-    rmhmc_kernel<R, Target, Metric, E, L, true><<<grid, block, 0, s>>>(a, tg);          \
+    rmhmc_kernel<R, Target, Metric, E, L, true><<<grid, block, (size_t)block * lay.epl * sizeof(R), s>>>(a, tg);          \
     GB_CHECK_LAUNCH();                                                                \
     return GB200_OK;                                                                  \
   }
@@ -19,7 +19,7 @@ static int launch_rmhmc_t(const TransArgs& a, const Target& tg, LayoutChoice lay
   }
 #define GB_X(E, L)                                                                    \
   if (lay.epl == E && lay.lpc == L) {                                                 \
-    rmhmc_kernel<R, Target, Metric, E, L, false><<<grid, block, 0, s>>>(a, tg);         \
+    rmhmc_kernel<R, Target, Metric, E, L, false><<<grid, block, (size_t)block * lay.epl * sizeof(R), s>>>(a, tg);         \
     GB_CHECK_LAUNCH();                                                                \
     return GB200_OK;                                                                  \
   }

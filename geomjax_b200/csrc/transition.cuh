@@ -17,6 +17,7 @@ struct TransArgs {
   double step_size;
   const void* step_size_per_chain;
   const void* inv_mass;
+  long long inv_mass_stride;  // 0: shared [D]; D: per chain [C, D]
   double alpha2;
   double divergence_threshold;
   double fp_tol, fp_div_tol;
@@ -41,6 +42,12 @@ __device__ __forceinline__ U2 transition_key(const TransArgs& a, long long chain
 // z = jax.random.normal(key, (D,)) distributed over the lane group (util.py:81-82).
 // Legacy threefry hashes the counters pairwise (i, i + D/2): when the layout is exact, D is
 // even and both halves of a pair live in the same lane, one block yields two normals.
+// The generation loop is deliberately NOT unrolled (threefry + erfinv is ~250 SASS instructions
+// per element; unrolling it EPL times blew the instruction cache: 45% stall_no_inst at EPL=25).
+// Values are staged through this thread's private column of shared memory so that the
+// register array z[] is still filled with static indices.
+extern __shared__ unsigned char gb_smem[];
+
 template <typename R, class LAY>
 __device__ __forceinline__ void draw_noise(const TransArgs& a, const LAY& lay, U2 key, long long chain,
                                            R (&z)[LAY::EPL]) {
@@ -51,24 +58,29 @@ __device__ __forceinline__ void draw_noise(const TransArgs& a, const LAY& lay, U
     for (int k = 0; k < EPL; ++k) z[k] = lay.valid(k) ? zo[lay.j(k)] : R(0);
     return;
   }
+  R* zs = (R*)gb_smem + threadIdx.x;
+  const int stride = blockDim.x;
   constexpr int DS = EPL * LPC;
   constexpr bool PAIRED = LAY::EXACT && (DS % 2 == 0) && ((DS / 2) % LPC == 0);
   if (PAIRED && a.mode == GB200_THREEFRY_LEGACY) {
     constexpr int HK = EPL / 2;  // slots per half
-#pragma unroll
-    for (int k = 0; k < HK; ++k) {
+#pragma unroll 1
+    for (int k = 0; k < HK; ++k) {  // 2 blocks = 4 normals in flight: threefry is a serial chain
       const uint32_t j = (uint32_t)lay.j(k);
       U2 o = threefry2x32(key.x, key.y, j, j + (uint32_t)(DS / 2));
-      z[k] = (R)bits_to_normal(o.x);
-      z[k + HK] = (R)bits_to_normal(o.y);
+      zs[k * stride] = (R)bits_to_normal(o.x);
+      zs[(k + HK) * stride] = (R)bits_to_normal(o.y);
     }
-    return;
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < EPL; ++k) {  // 4 independent threefry + erfinv chains in flight (ILP)
+      R v = R(0);
+      if (lay.valid(k)) v = (R)bits_to_normal(random_bits_elem(a.mode, key, (uint32_t)lay.j(k), (uint32_t)lay.D()));
+      zs[k * stride] = v;
+    }
   }
 #pragma unroll
-  for (int k = 0; k < EPL; ++k) {
-    z[k] = R(0);
-    if (lay.valid(k)) z[k] = (R)bits_to_normal(random_bits_elem(a.mode, key, (uint32_t)lay.j(k), (uint32_t)a.D));
-  }
+  for (int k = 0; k < EPL; ++k) z[k] = zs[k * stride];
 }
 
 // mcmc/proposal.py:87-121 (proposal_from_energy_diff) + :168-185 (static_binomial_sampling)

@@ -169,11 +169,14 @@ class _Engine:
             if isinstance(im, np.ndarray):
                 im = torch.from_numpy(im)
             im = im.to(device=ref.device, dtype=ref.dtype).contiguous()
-            if im.ndim != 1:
+            if im.ndim == 2 and im.shape == (ref.shape[0], self.target.D):
+                # batched (vmapped) form: one diagonal inverse mass matrix per chain
+                p.inverse_mass_per_chain = 1
+            elif im.ndim != 1:
                 # lmcmonge/metrics.py:145-153: only a diagonal (1-d) mass matrix is accepted
                 raise ValueError("The mass matrix has the wrong number of dimensions:"
                                  f" expected 1, got {im.ndim}.")
-            if im.shape[0] != self.target.D:
+            elif im.shape[0] != self.target.D:
                 raise ValueError("inverse_mass_matrix must have shape (D,)")
             p.inverse_mass_matrix = N.ptr(im)
             keep.append(im)

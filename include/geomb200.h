@@ -93,6 +93,8 @@ typedef struct gb200_kernel_params {
   const void* inverse_mass_matrix;   /* lmcmonge: [D] diagonal, NULL = ones */
   int32_t dtype;                     /* gb200_dtype */
   int32_t lanes_per_chain;           /* 0 = auto; else 1,2,4,8,16,32 (tuning knob) */
+  int32_t inverse_mass_per_chain;    /* lmcmonge: 0 = inverse_mass_matrix is [D]; 1 = [C, D] (vmapped window adaptation) */
+  int32_t reserved;
 } gb200_kernel_params;
 
 /* RMHMCState / LMCState (rmhmc/rmhmc.py:30-41, lmcmc/lmc.py:30-42, lmcmonge/lmc.py:32-44). */

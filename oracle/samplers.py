@@ -35,7 +35,30 @@ def _dot(a, b):
 
 
 def _solve(A, b):
-    return np.linalg.solve(A, b[..., None])[..., 0]
+    try:
+        return np.linalg.solve(A, b[..., None])[..., 0]
+    except np.linalg.LinAlgError:  # singular / non-finite member of the batch: NaN for that chain (JAX semantics)
+        out = np.full(b.shape, np.nan, b.dtype)
+        for c in range(A.shape[0]):
+            try:
+                out[c] = np.linalg.solve(A[c], b[c])
+            except np.linalg.LinAlgError:
+                pass
+        return out
+
+
+def _chol(A):
+    """Batched lower Cholesky; a non-positive-definite member yields NaN (as jnp does) instead of raising."""
+    try:
+        return np.linalg.cholesky(A)
+    except np.linalg.LinAlgError:
+        out = np.full(A.shape, np.nan, A.dtype)
+        for c in range(A.shape[0]):
+            try:
+                out[c] = np.linalg.cholesky(A[c])
+            except np.linalg.LinAlgError:
+                pass
+        return out
 
 
 class Info(NamedTuple):
@@ -101,8 +124,8 @@ def _rmhmc_kinetic(target, q, p):
     """rmhmc/metrics.py:60-74: -multivariate_normal.logpdf(p; 0, G(q)) through Cholesky."""
     dt = target.dtype
     G = target.metric(q)
-    Lc = np.linalg.cholesky(G)
-    y = np.stack([sla.solve_triangular(Lc[c], p[c], lower=True) for c in range(q.shape[0])])
+    Lc = _chol(G)
+    y = np.stack([sla.solve_triangular(Lc[c], p[c], lower=True, check_finite=False) for c in range(q.shape[0])])
     D = q.shape[1]
     logpdf = (dt.type(-0.5) * _dot(y, y) - dt.type(D / 2.0 * np.log(2 * np.pi))
               - np.log(np.diagonal(Lc, axis1=1, axis2=2)).sum(-1))
@@ -174,7 +197,7 @@ def rmhmc_step(keys, state, target, step_size, num_integration_steps, *,
     k_m, k_a = _draw_keys(keys, mode)
     zz = _normal(k_m, D, dt, mode, z)
     G = target.metric(q0)
-    p0 = _mv(np.linalg.cholesky(G), zz).astype(dt)      # rmhmc/metrics.py:45-58
+    p0 = _mv(_chol(G), zz).astype(dt)      # rmhmc/metrics.py:45-58
     v0 = _solve(G, p0).astype(dt)                        # :120-127
     H0 = (-l0 + _rmhmc_kinetic(target, q0, p0)).astype(dt)  # mcmc/metrics.py:160-166
     q, p, v, l, g = q0, p0, v0, l0, g0
@@ -231,7 +254,7 @@ def _grad_logdet_metric(target, q):
 
 
 def _lu_logdet(A):
-    lu, piv = sla.lu_factor(A)
+    lu, piv = sla.lu_factor(A, check_finite=False)  # NaN/inf are data (-> rejected), as in JAX
     d = np.diagonal(lu, axis1=-2, axis2=-1)
     with np.errstate(divide="ignore"):
         return (lu, piv), np.log(np.abs(d)).sum(-1).astype(A.dtype)
@@ -245,7 +268,7 @@ def _lmc_half_step(target, q, v, J, g, step_size):
     J = (J - ld).astype(dt)
     dphi = -g + dt.type(0.5) * _grad_logdet_metric(target, q)
     v_temp = (_mv(target.metric(q), v) - dt.type(0.5) * eps * dphi).astype(dt)
-    v_new = np.stack([sla.lu_solve((lu[c], piv[c]), v_temp[c]) for c in range(q.shape[0])]).astype(dt)
+    v_new = np.stack([sla.lu_solve((lu[c], piv[c]), v_temp[c], check_finite=False) for c in range(q.shape[0])]).astype(dt)
     _, ld2 = _lu_logdet(_omega_tilde(target, q, v_new, -eps))
     J = (J + ld2).astype(dt)
     return v_new, J
@@ -284,9 +307,9 @@ def lmc_step(keys, state, target, step_size, num_integration_steps, *,
     # velocity_generator lmcmc/metrics.py:75-91: sigma = L^-T via solve_triangular(L, I, trans)
     G = target.metric(q0)
     G = dt.type(0.5) * (G + G.transpose(0, 2, 1))
-    Lc = np.linalg.cholesky(G)
+    Lc = _chol(G)
     eye = np.eye(D, dtype=dt)
-    sig = np.stack([sla.solve_triangular(Lc[c], eye, lower=True, trans=1) for c in range(C)])
+    sig = np.stack([sla.solve_triangular(Lc[c], eye, lower=True, trans=1, check_finite=False) for c in range(C)])
     v0 = _mv(sig.astype(dt), zz).astype(dt)
     p0 = _mv(target.metric(q0), v0).astype(dt)           # lmcmc/lmc.py:168
     H0 = (-l0 + _lmc_kinetic(target, q0, v0) - J0).astype(dt)  # lmc_energy :209-221
@@ -405,7 +428,7 @@ def lmcmonge_step(keys, state, target, step_size, inverse_mass_matrix, num_integ
         # velocity_generator lmcmonge/metrics.py:155-166: dense Cholesky of G^-1
         inv_metric = (np.einsum("i,ij->ij", inv_mass, np.eye(D, dtype=dt))[None]
                       - dt.type(alpha2) * np.einsum("ci,cj->cij", dl_ig, dl_ig)).astype(dt)
-        Lc = np.linalg.cholesky(inv_metric)
+        Lc = _chol(inv_metric)
         v0 = _mv(Lc, zz).astype(dt)
         p0 = _monge_mvp(dt, alpha2, mass, v0, g0, L0)    # :202-204 (un-normalised grad, as written)
         Hv = (target.hvp(q0, v0) / sL).astype(dt)        # :206-208

@@ -1,0 +1,111 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol of include/geomb200.h; host-only
+entry points (diagnostics finalisation, flop model) against the oracle; facade error behaviour.
+No kernel is launched here."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import diagnostics as OD
+
+
+def _lib():
+    from geomjax_b200 import _native as N
+    return N, N.lib()
+
+
+def test_library_exports_every_header_symbol():
+    N, lib = _lib()
+    syms = N.header_symbols()
+    assert len(syms) >= 20
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(N.PROTOTYPES) == set(syms)
+    assert lib.gb200_version() == 100
+
+
+def test_struct_sizes_match_header_layout():
+    N, _ = _lib()
+    assert C.sizeof(N.State) == 32 and C.sizeof(N.Info) == 16 * 8
+    assert C.sizeof(N.KeySource) == 8 + 8 + 5 * 8
+    assert C.sizeof(N.TargetDesc) == 16 + 8 + 64 + 32
+    assert C.sizeof(N.KernelParams) == 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8
+
+
+def _ar1(T, Cn, D, rho, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((T, Cn, D))
+    for t in range(1, T):
+        x[t] = rho * x[t - 1] + x[t]
+    return x + rng.standard_normal((1, Cn, 1)) * 0.05
+
+
+def partial_stats(x):
+    """NumPy restatement of k_rhat_partial / k_ess_partial (chain-summed sufficient statistics)."""
+    T, Cn, D = x.shape
+    m = x.mean(0)
+    v = x.var(0, ddof=1)
+    stats = np.concatenate([m.sum(0), (m * m).sum(0), v.sum(0), [float(Cn)]])
+    cen = x - m[None]
+    acov = np.stack([(cen[: T - l] * cen[l:]).sum(0).sum(0) / T for l in range(T)])
+    return stats, acov
+
+
+@pytest.mark.parametrize("T,Cn,D,rho", [(200, 4, 3, 0.7), (101, 6, 2, 0.2), (64, 2, 1, 0.95)])
+def test_rhat_ess_finalize_match_oracle(T, Cn, D, rho):
+    N, lib = _lib()
+    x = _ar1(T, Cn, D, rho, seed=T)
+    stats, acov = partial_stats(x)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rhat = np.empty(D)
+    assert lib.gb200_rhat_finalize(dp(stats), T, D, dp(rhat)) == 0
+    np.testing.assert_allclose(rhat, np.atleast_1d(OD.potential_scale_reduction(x, 1, 0)), rtol=1e-10)
+    want = np.atleast_1d(OD.effective_sample_size(x, 1, 0))
+    ess = np.empty(D)
+    trunc = np.zeros(D, np.uint8)
+    a = np.ascontiguousarray(acov)
+    assert lib.gb200_ess_finalize(dp(a), dp(stats), T, Cn, D, T, dp(ess), trunc.ctypes.data_as(C.POINTER(C.c_uint8))) == 0
+    np.testing.assert_allclose(ess, want, rtol=1e-8)
+    # a truncated lag window gives the same answer as long as Geyer's sequence ended inside it
+    for lags in (8, 16, 32):
+        a = np.ascontiguousarray(acov[:lags])
+        assert lib.gb200_ess_finalize(dp(a), dp(stats), T, Cn, D, lags, dp(ess), trunc.ctypes.data_as(C.POINTER(C.c_uint8))) == 0
+        ok = trunc == 0
+        np.testing.assert_allclose(ess[ok], want[ok], rtol=1e-8)
+    assert lib.gb200_rhat_finalize(dp(stats), 1, D, dp(rhat)) < 0  # bad argument -> negative status + message
+    assert b"rhat_finalize" in lib.gb200_last_error()
+
+
+def test_flop_model_and_facade_errors():
+    import torch
+    import geomjax_b200 as g
+    N, lib = _lib()
+    t = g.neal_funnel(20)
+    d = t.c_struct()
+    assert lib.gb200_flops_per_chain_step(N.LMCMONGE, C.byref(d)) == 59 * 20 + 60
+    assert lib.gb200_flops_per_chain_step(N.LMC, C.byref(d)) == 25 * 20 + 140
+    with pytest.raises(ValueError):
+        g.neal_funnel(1)
+    with pytest.raises(NotImplementedError):
+        g.rmhmc(lambda x: -0.5 * (x ** 2).sum(), 0.1, lambda x: torch.eye(2), 4)
+    with pytest.raises(NotImplementedError):
+        g.lmc(t, 0.1, t, 4, integrator=lambda *a: None)
+    alg = g.lmc(t, 0.1, t.fisher_metric_fn, 4)
+    with pytest.raises(g._native.NativeError):
+        alg.init(torch.ones((3, 20)))  # CPU tensor: there is no CPU fallback
+    with pytest.raises(ValueError):
+        g.lmc(t, 0.1, g.neal_funnel(21), 4)  # metric of a different target
+
+
+def test_build_schedule_matches_reference_shape():
+    """adaptation/window_adaptation.py:360-450: Stan windows for the default 1000 steps."""
+    from geomjax_b200.adaptation import build_schedule
+    s = build_schedule(1000)
+    assert len(s) == 1000
+    assert s[:75] == [(0, False)] * 75 and s[-50:] == [(0, False)] * 50
+    ends = [i for i, (st, e) in enumerate(s) if e]
+    assert ends == [99, 149, 249, 449, 949]
+    assert all(st == 1 for st, _ in s[75:950])
+    assert build_schedule(10) == [(0, False)] * 10
+    s = build_schedule(100)
+    assert len(s) == 100 and [i for i, (_, e) in enumerate(s) if e] == [89]
