@@ -39,9 +39,13 @@ def _oracle_chunk(args):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     from oracle import prng as P, samplers as S, targets as Tg
     D = cfg["D"]
-    tgt = Tg.NealFunnel(D, cfg.get("sigma", 3.0))
+    if cfg["target"] == "logreg":
+        X, y = Tg.make_logreg_data(cfg["N"], D, cfg.get("data_seed", 0))
+        tgt = Tg.LogisticRegression(X, y, cfg["prior_precision"])
+    else:
+        tgt = Tg.NealFunnel(D, cfg.get("sigma", 3.0))
     root = P.key(cfg["root_key"])
-    q0 = np.ones((C, D), np.float32)
+    q0 = (np.ones if cfg["init_position"] == "ones" else np.zeros)((C, D), np.float32)
     idx = np.arange(chain_offset, chain_offset + C)
     if cfg["sampler"] == "lmcmonge":
         st = S.lmcmonge_init(q0, tgt)
@@ -82,7 +86,7 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    cpw = 2048 if cfg["sampler"] == "lmcmonge" else 64
+    cpw = 2048 if cfg["sampler"] == "lmcmonge" else (8 if cfg["target"] == "logreg" else 64)
     # calibrate the per-step sample so that warmup + steps finish within a few minutes
     v, wall = oracle_throughput(cfg, cpw, 1, cores)
     per_transition = wall
@@ -181,7 +185,13 @@ def run_ours(args, cfg):
     K, W = args.steps, args.warmup
     total_chains = C * world
     total_transitions = 1 << 20  # width of the outer split(root, T); fixed so that keys do not depend on K
-    target = g.neal_funnel(D, sigma=cfg.get("sigma", 3.0))
+    if cfg["target"] == "logreg":
+        from oracle.targets import make_logreg_data  # frozen synthetic design (input data only)
+        Xh, yh = make_logreg_data(cfg["N"], D, cfg.get("data_seed", 0))
+        target = g.logistic_regression(torch.from_numpy(Xh).to(dev), torch.from_numpy(yh).to(dev), cfg["prior_precision"])
+    else:
+        target = g.neal_funnel(D, sigma=cfg.get("sigma", 3.0))
+    init_fill = torch.ones if cfg["init_position"] == "ones" else torch.zeros
     root = g.random.PRNGKey(cfg["root_key"])
     if cfg["sampler"] == "lmcmonge":
         integ = {"omega": g.integrators.half_step_omega, "omega_fixed": g.integrators.half_step_omega_fixed,
@@ -219,7 +229,7 @@ def run_ours(args, cfg):
     fp32_peak_tflops = 2.0 * grid * block * iters / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
     # ---- device-resident arm
-    state = alg.init(torch.ones((C, D), device=dev))
+    state = alg.init(init_fill((C, D), device=dev))
     out_state = [torch.empty_like(t) for t in state]
 
     def fused(st, first):
@@ -254,7 +264,7 @@ def run_ours(args, cfg):
     accept_now = None
 
     # ---- e2e arm: host buffers, H2D + init + fused transitions + D2H inside the timed region
-    host_q = torch.ones((C, D)).pin_memory()
+    host_q = init_fill((C, D)).pin_memory()
     host_out = torch.empty((C, D)).pin_memory()
     host_acc = torch.empty((TPS, C)).pin_memory()
 
@@ -287,7 +297,7 @@ def run_ours(args, cfg):
     ess_info = {}
     if args.ess_samples > 0:
         Tn = args.ess_samples
-        st = alg.init(torch.ones((C, D), device=dev))
+        st = alg.init(init_fill((C, D), device=dev))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -312,6 +322,20 @@ def run_ours(args, cfg):
 
     if rank == 0:
         flops_unit = N.lib().gb200_flops_per_chain_step(sampler_id, target.c_struct())
+        fp_iters_per_step = None
+        if sampler_id == N.RMHMC:
+            # implicit midpoint: (2 + iters) evaluations of the fixed-point map per step; measure iters
+            ks = N.KeySource()
+            kk = g.random.chain_keys(root, 0, total_transitions, C, chain_offset=rank * C, total_chains=total_chains)
+            ks.keys, ks.num_transitions = N.ptr(kk), 1
+            _, inf = alg.step.engine.launch(state, ks, want_info=True, extra_info=True)
+            fp_iters_per_step = float(inf["fp_iters"].float().mean()) / L
+            if cfg["target"] == "logreg":
+                Nr = cfg["N"]
+                feval = 2.0 * Nr * D * D + 10.0 * Nr * D + D ** 3
+            else:
+                feval = 21.0 * D + 50.0
+            flops_unit = (2.0 + fp_iters_per_step) * feval
         med_ms = float(np.median(kernel_ms))
         ach = flops_unit * C * L * TPS / (med_ms * 1e-3) / 1e12
         peaks = {}
@@ -334,7 +358,7 @@ def run_ours(args, cfg):
                        "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
             "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                          "frac": ach / fp32_peak_tflops, "traffic": None,
-                         "flops_per_chain_step": flops_unit, "kernel_ms_median": med_ms,
+                         "flops_per_chain_step": flops_unit, "fp_iters_per_step": fp_iters_per_step, "kernel_ms_median": med_ms,
                          "peak_source": "measured in this process: FFMA microbenchmark kernel (148x8 CTAs x 256 thr, 8 independent FMA chains)",
                          "hbm": {"achieved_gbs": state_bytes / (med_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
@@ -347,7 +371,7 @@ def run_ours(args, cfg):
         }
         line.update(ess_info)
         if not args.no_cpu_baseline and world == 1:
-            cpw = 2048 if cfg["sampler"] == "lmcmonge" else 64
+            cpw = 2048 if cfg["sampler"] == "lmcmonge" else (8 if cfg["target"] == "logreg" else 64)
             v1, w1 = oracle_throughput(cfg, cpw, 1, 1)
             tr = max(1, min(64, int(12.0 / max(w1, 1e-3))))
             v, w = oracle_throughput(cfg, cpw, tr, 1)

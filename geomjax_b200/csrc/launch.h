@@ -12,6 +12,9 @@ void set_error(const char* fmt, ...);
 GB_DECL_LPC(1) GB_DECL_LPC(2) GB_DECL_LPC(4) GB_DECL_LPC(8) GB_DECL_LPC(32)
 #undef GB_DECL_LPC
 
+int launch_rmhmc_logreg(const TransArgs& a, const gb200_target_desc& t, int dtype, cudaStream_t s);
+int launch_init_logreg(const gb200_target_desc& t, gb200_state st, long long C, int dtype, cudaStream_t s);
+
 #define GB_BY_LPC(base, lay, ...)                          \
   switch ((lay).lpc) {                                     \
     case 1: return base##_lpc1(__VA_ARGS__);               \

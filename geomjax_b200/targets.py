@@ -57,6 +57,24 @@ def neal_funnel(D: int = 2, mean: float = 0.0, sigma: float = 3.0) -> TargetDesc
     return TargetDescriptor(N.TARGET_FUNNEL, D, (sigma,), name="neal_funnel")
 
 
+def logistic_regression(X, y, prior_precision: float = 0.01) -> TargetDescriptor:
+    """NEW built-in (BASELINE.json north_star): Bayesian logistic regression
+    l(theta) = sum_n [y_n eta_n - softplus(eta_n)] - alpha/2 |theta|^2, eta = X theta, with the
+    Fisher-information + prior metric G = X^T diag(s(1-s)) X + alpha I.  ``X``: (N, D) CUDA tensor,
+    ``y``: (N,) in {0, 1}.  The kernels read the transposed, 16-byte-padded copy made here."""
+    import torch
+    if X.ndim != 2 or y.ndim != 1 or y.shape[0] != X.shape[0]:
+        raise ValueError("logistic_regression needs X (N, D) and y (N,)")
+    Nrows, D = X.shape
+    ldx = (Nrows + 3) // 4 * 4
+    Xt = torch.zeros((D, ldx), dtype=torch.float32, device=X.device)
+    Xt[:, :Nrows] = X.t().to(torch.float32)
+    X = X.to(torch.float32).contiguous()
+    y = y.to(torch.float32).contiguous()
+    return TargetDescriptor(N.TARGET_LOGREG, D, (prior_precision, float(ldx)), N_rows=Nrows, X=X, y=y, vec0=Xt,
+                            name="logistic_regression")
+
+
 def as_target(obj) -> TargetDescriptor:
     if isinstance(obj, TargetDescriptor):
         return obj

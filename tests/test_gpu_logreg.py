@@ -1,0 +1,77 @@
+"""rmhmc on Bayesian logistic regression with the Fisher metric (dense per-chain metric, CTA per chain)
+against the dense NumPy oracle (same reference semantics, analytic derivatives)."""
+import numpy as np
+import pytest
+
+from oracle import samplers as S
+from oracle import targets as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(x, dev):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def _close(got, want, rtol, atol, what=""):
+    got = got.cpu().numpy() if hasattr(got, "cpu") else np.asarray(got)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, err_msg=what)
+
+
+@pytest.mark.parametrize("Nrows,D,C,L", [(40, 3, 9, 1), (200, 8, 20, 2), (1000, 25, 6, 1), (1000, 25, 4, 3), (333, 17, 5, 2)])
+def test_rmhmc_logreg_vs_oracle(cuda, Nrows, D, C, L):
+    import geomjax_b200 as g
+    X, y = T.make_logreg_data(Nrows, D, seed=1)
+    tgt = T.LogisticRegression(X, y, 0.01)
+    rng = np.random.default_rng(D)
+    q = (0.1 * rng.standard_normal((C, D))).astype(np.float32)
+    keys = rng.integers(0, 2 ** 32, size=(C, 2), dtype=np.uint64).astype(np.uint32)
+    eps = 0.1
+    ost = S.rmhmc_init(q, tgt)
+    onew, oinfo = S.rmhmc_step(keys, ost, tgt, eps, L)
+    target = g.logistic_regression(_t(X, cuda), _t(y, cuda), 0.01)
+    alg = g.rmhmc(target, eps, target, L)
+    st = alg.init(_t(q, cuda))
+    _close(st.logdensity, ost.logdensity, 1e-5, 1e-3, "init logdensity")
+    _close(st.logdensity_grad, ost.logdensity_grad, 1e-4, 1e-3, "init grad")
+    new, info = alg.step(_t(keys, cuda), st)
+    ok = oinfo.extra["fp_iters"] < 50 * L  # chains whose float32 fixed point stalls at tol=1e-6 are noise-level
+    assert oinfo.is_accepted.mean() > 0.5 and ok.mean() > 0.8
+    okt = _t(ok, cuda)
+    scale = float(np.abs(oinfo.momentum).max())
+    _close(info.momentum, oinfo.momentum, 1e-5, 3e-5 * scale, "momentum draw")
+    ps = info.proposal.state
+    _close(ps.position[okt], oinfo.proposal["position"][ok], 1e-4, 1e-5, "position")
+    _close(ps.momentum[okt], oinfo.proposal["momentum"][ok], 1e-4, 1e-4 * scale, "momentum")
+    _close(ps.velocity[okt], oinfo.proposal["velocity"][ok], 1e-4, 1e-5, "velocity")
+    _close(ps.logdensity[okt], oinfo.proposal["logdensity"][ok], 1e-5, 2e-3, "logdensity")
+    _close(info.energy[okt], oinfo.energy[ok], 1e-5, 3e-3, "energy")
+    _close(info.acceptance_rate[okt], oinfo.acceptance_rate[ok], 1e-2, 5e-3, "acceptance")
+    got_acc = info.is_accepted.cpu().numpy()
+    clear = np.abs(oinfo.extra["u"] - oinfo.acceptance_rate) > 2e-2
+    np.testing.assert_array_equal(got_acc[clear & ok], oinfo.is_accepted[clear & ok])
+    same = (got_acc == oinfo.is_accepted) & ok
+    _close(new.position[_t(same, cuda)], onew.position[same], 1e-4, 1e-5)
+
+
+def test_logreg_fused_equals_stepwise_and_limits(cuda):
+    import torch
+    import geomjax_b200 as g
+    X, y = T.make_logreg_data(120, 6, seed=3)
+    target = g.logistic_regression(_t(X, cuda), _t(y, cuda), 0.01)
+    alg = g.rmhmc(target, 0.1, target, 2)
+    st0 = alg.init(torch.zeros((33, 6), device=cuda))
+    root = g.random.PRNGKey(0)
+    st = st0
+    for t in range(3):
+        st, _ = alg.step(g.random.chain_keys(root, t, 3, 33), st)
+    fst, samples, _ = g.run_fused(alg.step, root, st0, 3, return_samples=True)
+    assert bool((fst.position == st.position).all()) and bool((samples[-1] == st.position).all())
+    # lmc / lmcmonge on logreg and designs that do not fit shared memory are refused loudly
+    with pytest.raises(g._native.NativeError):
+        g.lmc(target, 0.1, target, 2).step(g.random.chain_keys(root, 0, 3, 33), g.lmc.init(st0.position, target))
+    Xb, yb = T.make_logreg_data(4000, 30, seed=3)
+    big = g.logistic_regression(_t(Xb, cuda), _t(yb, cuda), 0.01)
+    with pytest.raises(g._native.NativeError):
+        g.rmhmc.init(torch.zeros((2, 30), device=cuda), big)
