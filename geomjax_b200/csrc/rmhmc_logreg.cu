@@ -43,11 +43,12 @@ struct LRSmem {
   // vec layout: 12 vectors of LR_DMAX
   __device__ float* v(int i) const { return vec + i * LR_DMAX; }
 };
-enum { V_Q = 0, V_P, V_Q0, V_P0, V_QN, V_PN, V_G, V_W, V_DT, V_Z, V_TMP, V_NUM };
+enum { V_Q = 0, V_P, V_Q0, V_P0, V_QN, V_PN, V_G, V_W, V_DT, V_Z, V_TMP, V_RINV, V_NUM };
 
 // logdensity, gradient and the metric pieces at position qv:
 //   fills wv (w), wpv (w'), rv (y - s); returns logp; grad -> gout; if need_metric: G, Cholesky L (in G),
 //   L^-1 (Li), logdet.
+template <int DP>
 __device__ float lr_eval(const LogRegDev& tg, const LRSmem& sm, const float* qv, float* gout, bool need_metric,
                          float* logdet_out) {
   const int N = tg.N, D = tg.D, ldx = tg.ldx, tid = threadIdx.x;
@@ -83,72 +84,118 @@ __device__ float lr_eval(const LogRegDev& tg, const LRSmem& sm, const float* qv,
     return lp;
   }
   // G_ij = sum_n w_n X[n,i] X[n,j] + alpha delta_ij : 4x4 register tiles, one warp per tile pair
-  const int nb = (D + 3) / 4;
-  const int ntiles = nb * (nb + 1) / 2;
-  for (int tI = warp; tI < ntiles; tI += LR_BLOCK / 32) {
+  // work item = (tile pair, half of the data rows): balances 2 * nb(nb+1)/2 items over the 8 warps
+  constexpr int nb = DP / 4;
+  constexpr int ntiles = nb * (nb + 1) / 2;
+  for (int i = tid; i < DP * sm.ldg; i += LR_BLOCK) {
+    const int r = i / sm.ldg, c = i - r * sm.ldg;
+    sm.G[i] = (r == c && r < DP) ? tg.alpha : 0.f;  // prior precision on the diagonal (also on padded dims)
+    sm.Li[i] = 0.f;                                  // staging buffer for the second half of the data rows
+  }
+  __syncthreads();
+  for (int wI = warp; wI < 2 * ntiles; wI += LR_BLOCK / 32) {
+    const int tI = wI >> 1, half = wI & 1;
     int ib = 0, rem = tI;
     while (rem >= nb - ib) { rem -= nb - ib; ++ib; }
     const int jb = ib + rem;
+    const int n_lo = half ? (N / 2) : 0, n_hi = half ? N : (N / 2);
     float acc[4][4];
 #pragma unroll
     for (int a_ = 0; a_ < 4; ++a_)
 #pragma unroll
       for (int b_ = 0; b_ < 4; ++b_) acc[a_][b_] = 0.f;
-    for (int n = lane; n < N; n += 32) {
+    for (int n = n_lo + lane; n < n_hi; n += 32) {
       const float w = sm.wv[n];
       float xi[4], xj[4];
 #pragma unroll
       for (int a_ = 0; a_ < 4; ++a_) {
         const int i = ib * 4 + a_, j = jb * 4 + a_;
-        xi[a_] = (i < D) ? sm.Xs[i * ldx + n] * w : 0.f;
-        xj[a_] = (j < D) ? sm.Xs[j * ldx + n] : 0.f;
+        xi[a_] = sm.Xs[i * ldx + n] * w;  // rows D..DP-1 of Xs are zero padding
+        xj[a_] = sm.Xs[j * ldx + n];
       }
 #pragma unroll
       for (int a_ = 0; a_ < 4; ++a_)
 #pragma unroll
         for (int b_ = 0; b_ < 4; ++b_) acc[a_][b_] = fmaf(xi[a_], xj[b_], acc[a_][b_]);
     }
+    // transpose-reduce: 16 values x 32 lanes -> lane pair (2e, 2e+1) holds total of element e
+    // (8+4+2+1+1 = 16 shuffles instead of 16 x 5)
+    float v16[16];
 #pragma unroll
     for (int a_ = 0; a_ < 4; ++a_)
 #pragma unroll
-      for (int b_ = 0; b_ < 4; ++b_) {
-        float v = acc[a_][b_];
+      for (int b_ = 0; b_ < 4; ++b_) v16[a_ * 4 + b_] = acc[a_][b_];
+    float v8[8], v4[4], v2[2];
+    {
+      const bool up = lane & 16;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const int i = ib * 4 + a_, j = jb * 4 + b_;
-        if (lane == 0 && i < D && j < D) {
-          const float gij = v + (i == j ? tg.alpha : 0.f);
-          sm.G[i * sm.ldg + j] = gij;
-          sm.G[j * sm.ldg + i] = gij;
-        }
+      for (int e = 0; e < 8; ++e) {
+        const float keep = up ? v16[e + 8] : v16[e], send = up ? v16[e] : v16[e + 8];
+        v8[e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
       }
+    }
+    {
+      const bool up = lane & 8;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float keep = up ? v8[e + 4] : v8[e], send = up ? v8[e] : v8[e + 4];
+        v4[e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+    }
+    {
+      const bool up = lane & 4;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float keep = up ? v4[e + 2] : v4[e], send = up ? v4[e] : v4[e + 2];
+        v2[e] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+    }
+    float v1;
+    {
+      const bool up = lane & 2;
+      const float keep = up ? v2[1] : v2[0], send = up ? v2[0] : v2[1];
+      v1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+    // element index held by this lane: bit4 -> +8, bit3 -> +4, bit2 -> +2, bit1 -> +1
+    const int e = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const int i = ib * 4 + (e >> 2), j = jb * 4 + (e & 3);
+    float* dst = half ? sm.Li : sm.G;  // the two row halves land in separate buffers (no atomics)
+    if ((lane & 1) == 0 && (ib != jb || i <= j)) {
+      dst[i * sm.ldg + j] += v1;
+      if (i != j) dst[j * sm.ldg + i] += v1;
+    }
   }
+  __syncthreads();
+  for (int i = tid; i < DP * sm.ldg; i += LR_BLOCK) sm.G[i] += sm.Li[i];
   __syncthreads();
   // Cholesky (lower, in place in G's lower triangle), one warp, lane = row
   if (warp == 0) {
-    for (int k = 0; k < D; ++k) {
-      float dkk = sm.G[k * sm.ldg + k];
+    // register-resident right-looking Cholesky: lane = row, the row lives in registers, column k of
+    // L is broadcast with shuffles (a shared-memory version spent 38% of the kernel in this serial
+    // section: every trailing update was a dependent LDS -> FMA -> STS chain).
+    float row[DP];
+#pragma unroll
+    for (int j = 0; j < DP; ++j) row[j] = (lane < DP) ? sm.G[lane * sm.ldg + j] : 0.f;
+    float diag = 1.f;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+      const float dkk = __shfl_sync(0xffffffffu, row[k], k);
       const float lkk = sqrtf(dkk);  // NaN for a non-positive pivot, as jnp's cholesky
-      __syncwarp();
-      if (lane == k) sm.G[k * sm.ldg + k] = lkk;
-      if (lane > k && lane < D) sm.G[lane * sm.ldg + k] /= lkk;
-      __syncwarp();
-      // trailing update: row = lane, columns k+1..lane
-      if (lane > k && lane < D) {
-        const float lik = sm.G[lane * sm.ldg + k];
-        for (int j = k + 1; j <= lane; ++j) sm.G[lane * sm.ldg + j] = fmaf(-lik, sm.G[j * sm.ldg + k], sm.G[lane * sm.ldg + j]);
-      }
-      __syncwarp();
-    }
-    // L^-1 by forward substitution, lane = column of the identity
-    if (lane < D) {
-      for (int i = 0; i < D; ++i) {
-        float s = (i == lane) ? 1.f : 0.f;
-        for (int k = lane; k < i; ++k) s = fmaf(-sm.G[i * sm.ldg + k], sm.Li[k * sm.ldg + lane], s);
-        sm.Li[i * sm.ldg + lane] = (i >= lane) ? s / sm.G[i * sm.ldg + i] : 0.f;
+      const float lik = (lane == k) ? lkk : row[k] * (1.f / lkk);
+      row[k] = lik;
+      if (lane == k) diag = lkk;
+#pragma unroll
+      for (int j = k + 1; j < DP; ++j) {
+        const float ljk = __shfl_sync(0xffffffffu, lik, j);
+        if (lane >= j) row[j] = fmaf(-lik, ljk, row[j]);
       }
     }
-    float ld = (lane < D) ? logf(sm.G[lane * sm.ldg + lane]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < DP; ++j)
+      if (lane < DP && j <= lane) sm.G[lane * sm.ldg + j] = row[j];
+    if (lane < DP) sm.v(V_RINV)[lane] = 1.f / diag;
+    float ld = (lane < D) ? logf(diag) : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
     if (lane == 0) *logdet_out = 2.f * ld;
@@ -157,43 +204,69 @@ __device__ float lr_eval(const LogRegDev& tg, const LRSmem& sm, const float* qv,
   return lp;
 }
 
-// w = G^-1 p = L^-T (L^-1 p) using Li; threads 0..D-1 (needs a block sync in between)
+// w = G^-1 p = L^-T (L^-1 p): two warp-parallel triangular solves (lane = row), warp 0 only
 __device__ void lr_solve(const LogRegDev& tg, const LRSmem& sm, const float* p, float* w) {
-  const int D = tg.D, tid = threadIdx.x;
-  float* tmp = sm.v(V_TMP);
-  if (tid < D) {
-    float s = 0.f;
-    for (int j = 0; j <= tid; ++j) s = fmaf(sm.Li[tid * sm.ldg + j], p[j], s);
-    tmp[tid] = s;
-  }
-  __syncthreads();
-  if (tid < D) {
-    float s = 0.f;
-    for (int k = tid; k < D; ++k) s = fmaf(sm.Li[k * sm.ldg + tid], tmp[k], s);
-    w[tid] = s;
+  const int D = tg.D, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    const float* rinv = sm.v(V_RINV);
+    float acc = (lane < D) ? p[lane] : 0.f;  // forward: L y = p
+    float y = 0.f;
+    for (int k = 0; k < D; ++k) {
+      const float yk = __shfl_sync(0xffffffffu, acc * rinv[k], k);
+      if (lane == k) y = yk;
+      if (lane > k && lane < D) acc = fmaf(-sm.G[lane * sm.ldg + k], yk, acc);
+    }
+    acc = y;  // backward: L^T x = y
+    float x = 0.f;
+    for (int k = D - 1; k >= 0; --k) {
+      const float xk = __shfl_sync(0xffffffffu, acc * rinv[k], k);
+      if (lane == k) x = xk;
+      if (lane < k) acc = fmaf(-sm.G[k * sm.ldg + lane], xk, acc);
+    }
+    if (lane < D) w[lane] = x;
   }
   __syncthreads();
 }
 
 // dT/dq_i = 1/2 sum_n w'_n x_ni (h_n - u_n^2)
+template <int DP>
 __device__ void lr_dTdq(const LogRegDev& tg, const LRSmem& sm, const float* w, float* dT) {
   const int N = tg.N, D = tg.D, ldx = tg.ldx, tid = threadIdx.x;
-  for (int n = tid; n < N; n += LR_BLOCK) {
-    float x[LR_DMAX];
+  const float* rinv = sm.v(V_RINV);
+  // two data rows per thread per pass: every L_ij fetched from shared memory feeds two independent
+  // FMA chains (halves the LDS count per FMA and hides the forward-substitution dependency chain)
+  for (int n = tid; n < N; n += 2 * LR_BLOCK) {
+    const int n2 = n + LR_BLOCK;
+    const bool has2 = n2 < N;
+    float xa[DP], xb[DP];  // become y = L^-1 x_n in place (padded dims stay 0)
 #pragma unroll
-    for (int i = 0; i < LR_DMAX; ++i) x[i] = (i < D) ? sm.Xs[i * ldx + n] : 0.f;
-    float u = 0.f, h = 0.f;
-#pragma unroll
-    for (int i = 0; i < LR_DMAX; ++i) {
-      if (i < D) {
-        u = fmaf(x[i], w[i], u);
-        float yk = 0.f;  // (L^-1 x)_i
-#pragma unroll
-        for (int j = 0; j <= i; ++j) yk = fmaf(sm.Li[i * sm.ldg + j], x[j], yk);
-        h = fmaf(yk, yk, h);
-      }
+    for (int i = 0; i < DP; ++i) {
+      xa[i] = (i < D) ? sm.Xs[i * ldx + n] : 0.f;
+      xb[i] = (i < D && has2) ? sm.Xs[i * ldx + n2] : 0.f;
     }
-    sm.rv[n] = sm.wpv[n] * (h - u * u);
+    float ua = 0.f, ub = 0.f, ha = 0.f, hb = 0.f;
+#pragma unroll
+    for (int i = 0; i < DP; ++i) {
+      const float wi = (i < D) ? w[i] : 0.f;
+      ua = fmaf(xa[i], wi, ua);
+      ub = fmaf(xb[i], wi, ub);
+    }
+#pragma unroll
+    for (int i = 0; i < DP; ++i) {
+      float sa = xa[i], sb = xb[i];
+#pragma unroll
+      for (int j = 0; j < i; ++j) {
+        const float lij = sm.G[i * sm.ldg + j];
+        sa = fmaf(-lij, xa[j], sa);
+        sb = fmaf(-lij, xb[j], sb);
+      }
+      xa[i] = sa * rinv[i];
+      xb[i] = sb * rinv[i];
+      ha = fmaf(xa[i], xa[i], ha);
+      hb = fmaf(xb[i], xb[i], hb);
+    }
+    sm.rv[n] = sm.wpv[n] * (ha - ua * ua);
+    if (has2) sm.rv[n2] = sm.wpv[n2] * (hb - ub * ub);
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
@@ -208,6 +281,7 @@ __device__ void lr_dTdq(const LogRegDev& tg, const LRSmem& sm, const float* w, f
 }
 
 // fixed-point map (rmhmc/integrators.py:119-142): (q, p) -> (qi + he w, pi - he (dT/dq - grad))
+template <int DP>
 __device__ void lr_map(const LogRegDev& tg, const LRSmem& sm, const float* q, const float* p, const float* qi,
                        const float* pi, float he, float* qn, float* pn) {
   float ld;
@@ -215,10 +289,10 @@ __device__ void lr_map(const LogRegDev& tg, const LRSmem& sm, const float* q, co
   float* w = sm.v(V_W);
   float* dT = sm.v(V_DT);
   __shared__ float ld_s;
-  lr_eval(tg, sm, q, g, true, &ld_s);
+  lr_eval<DP>(tg, sm, q, g, true, &ld_s);
   (void)ld;
   lr_solve(tg, sm, p, w);
-  lr_dTdq(tg, sm, w, dT);
+  lr_dTdq<DP>(tg, sm, w, dT);
   const int tid = threadIdx.x;
   if (tid < tg.D) {
     const float a = qi[tid], b = pi[tid];  // read before write: qn/pn may alias qi/pi
@@ -270,6 +344,7 @@ __device__ void lr_stage_X(const LogRegDev& tg, const LRSmem& sm) {
                    : "memory");
     }
   }
+  for (int i = tg.D * tg.ldx + threadIdx.x; i < (tg.D + 3) / 4 * 4 * tg.ldx; i += blockDim.x) sm.Xs[i] = 0.f;  // padding rows
   unsigned done = 0;
   while (!done) {
     asm volatile(
@@ -284,7 +359,7 @@ __device__ void lr_stage_X(const LogRegDev& tg, const LRSmem& sm) {
 __device__ LRSmem lr_carve(const LogRegDev& tg, unsigned char* base) {
   LRSmem sm;
   float* f = (float*)base;
-  sm.Xs = f; f += (size_t)tg.D * tg.ldx;
+  sm.Xs = f; f += (size_t)((tg.D + 3) / 4 * 4) * tg.ldx;
   sm.wv = f; f += tg.ldx;
   sm.wpv = f; f += tg.ldx;
   sm.rv = f; f += tg.ldx;
@@ -297,9 +372,10 @@ __device__ LRSmem lr_carve(const LogRegDev& tg, unsigned char* base) {
 }
 
 static size_t lr_smem_bytes(int D, int ldx) {
-  return sizeof(float) * ((size_t)D * ldx + 3 * (size_t)ldx + 2 * LR_DMAX * (LR_DMAX + 1) + V_NUM * LR_DMAX + 64);
+  return sizeof(float) * ((size_t)((D + 3) / 4 * 4) * ldx + 3 * (size_t)ldx + 2 * LR_DMAX * (LR_DMAX + 1) + V_NUM * LR_DMAX + 64);
 }
 
+template <int DP>
 __global__ void __launch_bounds__(LR_BLOCK, 1) rmhmc_logreg_kernel(const TransArgs a, const LogRegDev tg) {
   extern __shared__ __align__(128) unsigned char lr_smem[];
   const LRSmem sm = lr_carve(tg, lr_smem);
@@ -339,7 +415,7 @@ __global__ void __launch_bounds__(LR_BLOCK, 1) rmhmc_logreg_kernel(const TransAr
       }
       __syncthreads();
       // metric at the start: momentum p = L z (rmhmc/metrics.py:45-58), H0 = -l0 + T(q, p)
-      lr_eval(tg, sm, q, g, true, &logdet_s);
+      lr_eval<DP>(tg, sm, q, g, true, &logdet_s);
       if (tid < D) {
         float s = 0.f;
         for (int j = 0; j <= tid; ++j) s = fmaf(sm.G[tid * sm.ldg + j], z[j], s);
@@ -358,23 +434,23 @@ __global__ void __launch_bounds__(LR_BLOCK, 1) rmhmc_logreg_kernel(const TransAr
       for (int s = 0; s < a.num_steps; ++s) {
         if (tid < D) { q0[tid] = q[tid]; p0[tid] = p[tid]; }
         __syncthreads();
-        lr_map(tg, sm, q0, p0, q0, p0, he, q, p);
+        lr_map<DP>(tg, sm, q0, p0, q0, p0, he, q, p);
         float nrm = lr_norm(tg, sm, q, p, q0, p0);
         int n = 0;
         while ((n < a.fp_max_iters) && (nrm < __int_as_float(0x7f800000)) && (nrm < div_tol) && (nrm > tol)) {
-          lr_map(tg, sm, q, p, q0, p0, he, qn, pn);
+          lr_map<DP>(tg, sm, q, p, q0, p0, he, qn, pn);
           nrm = lr_norm(tg, sm, qn, pn, q, p);
           if (tid < D) { q[tid] = qn[tid]; p[tid] = pn[tid]; }
           __syncthreads();
           ++n;
         }
         iters_total += n;
-        lr_map(tg, sm, q, p, q, p, he, qn, pn);  // explicit update from the midpoint
+        lr_map<DP>(tg, sm, q, p, q, p, he, qn, pn);  // explicit update from the midpoint
         if (tid < D) { q[tid] = qn[tid]; p[tid] = pn[tid]; }
         __syncthreads();
       }
       // end state
-      const float lp = lr_eval(tg, sm, q, g, true, &logdet_s);
+      const float lp = lr_eval<DP>(tg, sm, q, g, true, &logdet_s);
       lr_solve(tg, sm, p, w);
       __shared__ float H1_s;
       __shared__ int acc_s;
@@ -419,6 +495,7 @@ __global__ void __launch_bounds__(LR_BLOCK, 1) rmhmc_logreg_kernel(const TransAr
   (void)go_s;
 }
 
+template <int DP>
 __global__ void __launch_bounds__(LR_BLOCK, 1) init_logreg_kernel(const LogRegDev tg, gb200_state st, long long C) {
   extern __shared__ __align__(128) unsigned char lr_smem[];
   const LRSmem sm = lr_carve(tg, lr_smem);
@@ -428,7 +505,7 @@ __global__ void __launch_bounds__(LR_BLOCK, 1) init_logreg_kernel(const LogRegDe
   for (long long chain = blockIdx.x; chain < C; chain += gridDim.x) {
     if (threadIdx.x < tg.D) q[threadIdx.x] = ((const float*)st.position)[chain * tg.D + threadIdx.x];
     __syncthreads();
-    const float lp = lr_eval(tg, sm, q, g, false, &dummy);
+    const float lp = lr_eval<DP>(tg, sm, q, g, false, &dummy);
     if (threadIdx.x < tg.D) ((float*)st.logdensity_grad)[chain * tg.D + threadIdx.x] = g[threadIdx.x];
     if (threadIdx.x == 0) {
       ((float*)st.logdensity)[chain] = lp;
@@ -463,12 +540,20 @@ int launch_rmhmc_logreg(const TransArgs& a, const gb200_target_desc& t, int dtyp
   size_t smem;
   int rc = lr_setup(t, &tg, &smem);
   if (rc) return rc;
-  cudaError_t e = cudaFuncSetAttribute(rmhmc_logreg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("logreg: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
   const int grid = (int)(a.C < 148 ? a.C : 148);
-  rmhmc_logreg_kernel<<<grid, LR_BLOCK, smem, s>>>(a, tg);
-  GB_CHECK_LAUNCH();
-  return GB200_OK;
+  const int dp = (tg.D + 3) / 4 * 4;
+#define GB_LR(DPV)                                                                                              \
+  if (dp == DPV) {                                                                                              \
+    cudaError_t e = cudaFuncSetAttribute(rmhmc_logreg_kernel<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) { set_error("logreg: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }            \
+    rmhmc_logreg_kernel<DPV><<<grid, LR_BLOCK, smem, s>>>(a, tg);                                               \
+    GB_CHECK_LAUNCH();                                                                                          \
+    return GB200_OK;                                                                                            \
+  }
+  GB_LR(4) GB_LR(8) GB_LR(12) GB_LR(16) GB_LR(20) GB_LR(24) GB_LR(28) GB_LR(32)
+#undef GB_LR
+  set_error("logreg: unsupported D");
+  return GB200_ERR_UNSUPPORTED;
 }
 
 int launch_init_logreg(const gb200_target_desc& t, gb200_state st, long long C, int dtype, cudaStream_t s) {
@@ -477,10 +562,10 @@ int launch_init_logreg(const gb200_target_desc& t, gb200_state st, long long C, 
   size_t smem;
   int rc = lr_setup(t, &tg, &smem);
   if (rc) return rc;
-  cudaError_t e = cudaFuncSetAttribute(init_logreg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(init_logreg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("logreg: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
   const int grid = (int)(C < 148 ? C : 148);
-  init_logreg_kernel<<<grid, LR_BLOCK, smem, s>>>(tg, st, C);
+  init_logreg_kernel<4><<<grid, LR_BLOCK, smem, s>>>(tg, st, C);  // no metric needed: DP is irrelevant
   GB_CHECK_LAUNCH();
   return GB200_OK;
 }
