@@ -123,6 +123,7 @@ static int check_target(const gb200_target_desc* t) {
   if (t->D < 1) { set_error("target: D must be >= 1"); return GB200_ERR_INVALID_ARGUMENT; }
   if (t->kind == GB200_TARGET_FUNNEL && t->D < 2) { set_error("funnel: D must be >= 2"); return GB200_ERR_INVALID_ARGUMENT; }
   if (t->kind == GB200_TARGET_BANANA && t->D != 2) { set_error("banana: D must be 2"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (t->kind == GB200_TARGET_GAUSSIAN && (!t->vec0 || !t->vec1)) { set_error("gaussian: needs vec0 = mean[D] and vec1 = precision[D]"); return GB200_ERR_INVALID_ARGUMENT; }
   return GB200_OK;
 }
 

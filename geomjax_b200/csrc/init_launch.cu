@@ -52,6 +52,16 @@ int GB_LPC_NAME(launch_init)(const gb200_target_desc& t, gb200_state st, long lo
       tg.setup(t);
       return launch_init_t<float>(tg, st, C, t.D, lay, s);
     }
+    case GB200_TARGET_GAUSSIAN: {
+      GaussianDiag<float> tg;
+      tg.setup(t);
+      return launch_init_t<float>(tg, st, C, t.D, lay, s);
+    }
+    case GB200_TARGET_BANANA: {
+      Banana<float> tg;
+      tg.setup(t);
+      return launch_init_t<float>(tg, st, C, t.D, lay, s);
+    }
     default:
       set_error("init: target kind %d has no in-kernel implementation", t.kind);
       return GB200_ERR_UNSUPPORTED;

@@ -246,3 +246,44 @@ __global__ void __launch_bounds__(128) lmc_kernel(const TransArgs a, const Targe
 }
 
 }  // namespace gb
+
+namespace gb {
+// Constant diagonal metric taken from the target (metric_fn returning a (D,) array: the ndim == 1
+// branches of lmcmc/metrics.py:82-83,100-104,166-171,186,194): Omega_tilde = diag(G), all volume
+// terms cancel, velocity = z / sqrt(G).
+template <typename R, class Target>
+struct TargetDiagMetric {
+  template <class LAY>
+  static __device__ __forceinline__ void draw(const LAY& lay, const Target& tg, const typename Target::Ctx&,
+                                              const R (&)[LAY::EPL], const R (&z)[LAY::EPL], R (&u)[LAY::EPL]) {
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) u[k] = z[k] * fast_rsqrt(tg.metric_diag(lay, k));
+  }
+  template <class LAY>
+  static __device__ __forceinline__ R kinetic(const LAY& lay, const Target& tg, const typename Target::Ctx&,
+                                              const R (&)[LAY::EPL], const R (&u)[LAY::EPL]) {
+    R p[2] = {R(0), R(0)};
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) {
+      const R G = tg.metric_diag(lay, k);
+      p[0] += log(G);
+      p[1] += G * u[k] * u[k];
+    }
+    group_sum_n<LAY::LPC>(p);
+    return R(-0.5) * p[0] + R(0.5) * p[1];
+  }
+  template <class LAY>
+  static __device__ __forceinline__ void Gv(const LAY& lay, const Target& tg, const typename Target::Ctx&,
+                                            const R (&)[LAY::EPL], const R (&u)[LAY::EPL], R (&p)[LAY::EPL]) {
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) p[k] = tg.metric_diag(lay, k) * u[k];
+  }
+  template <class LAY>
+  static __device__ __forceinline__ R half_step(const LAY& lay, const Target& tg, const typename Target::Ctx&,
+                                                const R (&)[LAY::EPL], const R (&g)[LAY::EPL], R (&u)[LAY::EPL], R eps) {
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) u[k] = fma(R(0.5) * eps, g[k] / tg.metric_diag(lay, k), u[k]);
+    return R(0);
+  }
+};
+}  // namespace gb

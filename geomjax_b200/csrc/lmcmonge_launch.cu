@@ -3,11 +3,12 @@
 
 namespace gb {
 
-template <typename R, class Target>
+template <typename R, class Target, bool ALLOW_EXACT>
 static int launch_lmcmonge_t(const TransArgs& a, const Target& tg, LayoutChoice lay, cudaStream_t s) {
   int grid, block;
   launch_shape(a.C, lay.lpc, &grid, &block);
   const bool unit = a.inv_mass == nullptr;
+  if constexpr (ALLOW_EXACT) {
 #define GB_XE(E, L)                                                                         \
   if (lay.epl == E && lay.lpc == L && a.D == E * L) {                                       \
     if (unit) lmcmonge_kernel<R, Target, E, L, true, true><<<grid, block, (size_t)block * lay.epl * sizeof(R), s>>>(a, tg);   \
@@ -17,6 +18,7 @@ static int launch_lmcmonge_t(const TransArgs& a, const Target& tg, LayoutChoice 
   }
   GB_MY_EXACT(GB_XE)
 #undef GB_XE
+  }
 #define GB_X(E, L)                                                                    \
   if (lay.epl == E && lay.lpc == L) {                                                 \
     lmcmonge_kernel<R, Target, E, L, false, false><<<grid, block, (size_t)block * lay.epl * sizeof(R), s>>>(a, tg);     \
@@ -38,8 +40,24 @@ int GB_LPC_NAME(launch_lmcmonge)(const TransArgs& a, const gb200_target_desc& t,
     case GB200_TARGET_FUNNEL: {
       Funnel<float> tg;
       tg.setup(t);
-      return launch_lmcmonge_t<float>(a, tg, lay, s);
+      return launch_lmcmonge_t<float, Funnel<float>, true>(a, tg, lay, s);
     }
+    case GB200_TARGET_GAUSSIAN: {
+      GaussianDiag<float> tg;
+      tg.setup(t);
+      return launch_lmcmonge_t<float, GaussianDiag<float>, false>(a, tg, lay, s);
+    }
+#if GB_LPC == 1
+    case GB200_TARGET_BANANA: {
+      Banana<float> tg;
+      tg.setup(t);
+      int grid, block;
+      launch_shape(a.C, 1, &grid, &block);
+      lmcmonge_kernel<float, Banana<float>, 2, 1, false, false><<<grid, block, (size_t)block * 2 * sizeof(float), s>>>(a, tg);
+      GB_CHECK_LAUNCH();
+      return GB200_OK;
+    }
+#endif
     default:
       set_error("lmcmonge: target kind %d has no in-kernel implementation", t.kind);
       return GB200_ERR_UNSUPPORTED;

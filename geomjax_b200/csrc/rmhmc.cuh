@@ -282,3 +282,42 @@ __global__ void __launch_bounds__(128) rmhmc_kernel(const TransArgs a, const Tar
 }
 
 }  // namespace gb
+
+namespace gb {
+// Constant diagonal metric from the target (ndim == 1 branches of rmhmc/metrics.py:47-48,63-65,123-124).
+template <typename R, class Target>
+struct TargetDiagMetricH {
+  template <class LAY>
+  static __device__ __forceinline__ void draw(const LAY& lay, const Target& tg, const typename Target::Ctx&,
+                                              const R (&)[LAY::EPL], const R (&z)[LAY::EPL], R (&p)[LAY::EPL]) {
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) p[k] = sqrt(tg.metric_diag(lay, k)) * z[k];
+  }
+  template <class LAY>
+  static __device__ __forceinline__ R Ginv(const LAY& lay, const Target& tg, const typename Target::Ctx&,
+                                           const R (&)[LAY::EPL], const R (&p)[LAY::EPL], R (&w)[LAY::EPL]) {
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) w[k] = p[k] / tg.metric_diag(lay, k);
+    return R(0);
+  }
+  template <class LAY>
+  static __device__ __forceinline__ void dTdq(const LAY&, const Target&, const typename Target::Ctx&,
+                                              const R (&)[LAY::EPL], const R (&)[LAY::EPL], R, R (&d)[LAY::EPL]) {
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) d[k] = R(0);
+  }
+  template <class LAY>
+  static __device__ __forceinline__ R kinetic(const LAY& lay, const Target& tg, const typename Target::Ctx&,
+                                              const R (&)[LAY::EPL], const R (&p)[LAY::EPL]) {
+    R s[2] = {R(0), R(0)};
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) {
+      const R G = tg.metric_diag(lay, k);
+      s[0] += p[k] * p[k] / G;
+      s[1] += log(G);
+    }
+    group_sum_n<LAY::LPC>(s);
+    return R(0.5) * s[0] + R(0.5) * s[1] + R(0.91893853320467274178) * (R)lay.D();
+  }
+};
+}  // namespace gb

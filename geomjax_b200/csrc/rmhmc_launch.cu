@@ -42,6 +42,24 @@ int GB_LPC_NAME(launch_rmhmc)(const TransArgs& a, const gb200_target_desc& t, La
         return launch_rmhmc_t<float, Funnel<float>, IdentityMetricH<float, Funnel<float>>, false>(a, tg, lay, s);
       return launch_rmhmc_t<float, Funnel<float>, FunnelArrowH<float>, true>(a, tg, lay, s);
     }
+    case GB200_TARGET_GAUSSIAN: {
+      GaussianDiag<float> tg;
+      tg.setup(t);
+      if (t.metric == GB200_METRIC_IDENTITY)
+        return launch_rmhmc_t<float, GaussianDiag<float>, IdentityMetricH<float, GaussianDiag<float>>, false>(a, tg, lay, s);
+      return launch_rmhmc_t<float, GaussianDiag<float>, TargetDiagMetricH<float, GaussianDiag<float>>, false>(a, tg, lay, s);
+    }
+#if GB_LPC == 1
+    case GB200_TARGET_BANANA: {
+      Banana<float> tg;
+      tg.setup(t);
+      int grid, block;
+      launch_shape(a.C, 1, &grid, &block);
+      rmhmc_kernel<float, Banana<float>, IdentityMetricH<float, Banana<float>>, 2, 1, false><<<grid, block, (size_t)block * 2 * sizeof(float), s>>>(a, tg);
+      GB_CHECK_LAUNCH();
+      return GB200_OK;
+    }
+#endif
     default:
       set_error("rmhmc: target kind %d has no in-kernel implementation", t.kind);
       return GB200_ERR_UNSUPPORTED;

@@ -147,3 +147,112 @@ struct Funnel {
 };
 
 }  // namespace gb
+
+namespace gb {
+
+// Diagonal Gaussian (NEW built-in): l = -1/2 sum_j prec_j (q_j - mean_j)^2,
+// constant metric diag(prec).  mean / prec are read through the read-only path on every use.
+template <typename R>
+struct GaussianDiag {
+  const R* mean;
+  const R* prec;
+  struct Ctx { R quad; };
+
+  __host__ void setup(const gb200_target_desc& t) {
+    mean = (const R*)t.vec0;
+    prec = (const R*)t.vec1;
+  }
+  template <class LAY>
+  __device__ __forceinline__ R mu(const LAY& lay, int k) const { return lay.valid(k) ? __ldg(mean + lay.j(k)) : R(0); }
+  template <class LAY>
+  __device__ __forceinline__ R metric_diag(const LAY& lay, int k) const { return lay.valid(k) ? __ldg(prec + lay.j(k)) : R(1); }
+
+  template <class LAY>
+  __device__ __forceinline__ Ctx prepare(const LAY& lay, const R (&q)[LAY::EPL]) const {
+    Acc4<R, LAY::EPL> s;
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) {
+      const R d = lay.valid(k) ? q[k] - mu(lay, k) : R(0);
+      s.fma(k, d * metric_diag(lay, k), d);
+    }
+    Ctx c;
+    c.quad = group_sum<LAY::LPC>(s.total());
+    return c;
+  }
+  __device__ __forceinline__ R logp(const Ctx& c) const { return R(-0.5) * c.quad; }
+  template <class LAY>
+  __device__ __forceinline__ void grad(const LAY& lay, const Ctx&, const R (&q)[LAY::EPL], R (&g)[LAY::EPL]) const {
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) g[k] = lay.valid(k) ? -metric_diag(lay, k) * (q[k] - mu(lay, k)) : R(0);
+  }
+  template <class LAY>
+  __device__ __forceinline__ void hvp(const LAY& lay, const Ctx&, const R (&)[LAY::EPL], const R (&u)[LAY::EPL], R s,
+                                      R (&o)[LAY::EPL]) const {
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) o[k] = lay.valid(k) ? -metric_diag(lay, k) * u[k] * s : R(0);
+  }
+  template <class LAY>
+  __device__ __forceinline__ void hvp2(const LAY& lay, const Ctx& c, const R (&q)[LAY::EPL], const R (&u1)[LAY::EPL],
+                                       const R (&u2)[LAY::EPL], R s, R (&o1)[LAY::EPL], R (&o2)[LAY::EPL]) const {
+    hvp(lay, c, q, u1, s, o1);
+    hvp(lay, c, q, u2, s, o2);
+  }
+};
+
+// Banana (NEW built-in; Haario's twisted Gaussian), D = 2:
+//   l = -x1^2 / (2 s1) - (x2 - b (x1^2 - s1))^2 / 2,  identity metric.
+template <typename R>
+struct Banana {
+  R s1, inv_s1, b;
+  struct Ctx { R x1, x2, r; };
+
+  __host__ void setup(const gb200_target_desc& t) {
+    s1 = (R)t.params[0];
+    inv_s1 = (R)(1.0 / t.params[0]);
+    b = (R)t.params[1];
+  }
+  template <class LAY>
+  __device__ __forceinline__ void pair(const LAY& lay, const R (&v)[LAY::EPL], R& a0, R& a1) const {
+    R p[2] = {R(0), R(0)};
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) {
+      p[0] += (lay.j(k) == 0) ? v[k] : R(0);
+      p[1] += (lay.j(k) == 1) ? v[k] : R(0);
+    }
+    group_sum_n<LAY::LPC>(p);
+    a0 = p[0];
+    a1 = p[1];
+  }
+  template <class LAY>
+  __device__ __forceinline__ Ctx prepare(const LAY& lay, const R (&q)[LAY::EPL]) const {
+    Ctx c;
+    pair(lay, q, c.x1, c.x2);
+    c.r = c.x2 - b * (c.x1 * c.x1 - s1);
+    return c;
+  }
+  __device__ __forceinline__ R logp(const Ctx& c) const { return -c.x1 * c.x1 * (R(0.5) * inv_s1) - R(0.5) * c.r * c.r; }
+  template <class LAY>
+  __device__ __forceinline__ void grad(const LAY& lay, const Ctx& c, const R (&)[LAY::EPL], R (&g)[LAY::EPL]) const {
+    const R g0 = -c.x1 * inv_s1 + R(2) * b * c.x1 * c.r;
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) g[k] = (lay.j(k) == 0) ? g0 : ((lay.j(k) == 1) ? -c.r : R(0));
+  }
+  template <class LAY>
+  __device__ __forceinline__ void hvp(const LAY& lay, const Ctx& c, const R (&)[LAY::EPL], const R (&u)[LAY::EPL], R s,
+                                      R (&o)[LAY::EPL]) const {
+    R u1, u2;
+    pair(lay, u, u1, u2);
+    const R h00 = -inv_s1 + R(2) * b * c.r - R(4) * b * b * c.x1 * c.x1, h01 = R(2) * b * c.x1;
+    const R o0 = (h00 * u1 + h01 * u2) * s, o1 = (h01 * u1 - u2) * s;
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) o[k] = (lay.j(k) == 0) ? o0 : ((lay.j(k) == 1) ? o1 : R(0));
+  }
+  template <class LAY>
+  __device__ __forceinline__ void hvp2(const LAY& lay, const Ctx& c, const R (&q)[LAY::EPL], const R (&u1)[LAY::EPL],
+                                       const R (&u2)[LAY::EPL], R s, R (&o1)[LAY::EPL], R (&o2)[LAY::EPL]) const {
+    hvp(lay, c, q, u1, s, o1);
+    hvp(lay, c, q, u2, s, o2);
+  }
+};
+
+}  // namespace gb

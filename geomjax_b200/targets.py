@@ -57,6 +57,22 @@ def neal_funnel(D: int = 2, mean: float = 0.0, sigma: float = 3.0) -> TargetDesc
     return TargetDescriptor(N.TARGET_FUNNEL, D, (sigma,), name="neal_funnel")
 
 
+def gaussian(mean, precision_diag) -> TargetDescriptor:
+    """NEW built-in: l = -1/2 sum_j prec_j (q_j - mean_j)^2 with the constant
+    metric diag(prec) (a (D,)-shaped ``metric_fn`` in the reference's terms).  CUDA tensors (D,)."""
+    import torch
+    mean = mean.to(torch.float32).contiguous()
+    prec = precision_diag.to(torch.float32).contiguous()
+    if mean.ndim != 1 or prec.shape != mean.shape:
+        raise ValueError("gaussian needs mean (D,) and precision_diag (D,)")
+    return TargetDescriptor(N.TARGET_GAUSSIAN, mean.shape[0], (), vec0=mean, vec1=prec, name="gaussian")
+
+
+def banana(sigma1_sq: float = 100.0, b: float = 0.03) -> TargetDescriptor:
+    """NEW built-in, D = 2: l = -x1^2/(2 s1) - (x2 - b (x1^2 - s1))^2 / 2; identity metric."""
+    return TargetDescriptor(N.TARGET_BANANA, 2, (sigma1_sq, b), metric=N.METRIC_IDENTITY, name="banana")
+
+
 def logistic_regression(X, y, prior_precision: float = 0.01) -> TargetDescriptor:
     """NEW built-in (BASELINE.json north_star): Bayesian logistic regression
     l(theta) = sum_n [y_n eta_n - softplus(eta_n)] - alpha/2 |theta|^2, eta = X theta, with the

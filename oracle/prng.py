@@ -141,15 +141,61 @@ _ERFINV_GE5 = np.array([-0.000200214257, 0.000100950558, 0.00134934322, -0.00367
                         2.83297682], dtype=np.float32)
 
 
+_LG1, _LG2, _LG3, _LG4 = (np.float32(0xAAAAAA / 2.0 ** 24), np.float32(0xCCCE13 / 2.0 ** 25),
+                          np.float32(0x91E9EE / 2.0 ** 25), np.float32(0xF89E26 / 2.0 ** 26))
+_LN2_HI, _LN2_LO = np.float32(6.9313812256e-01), np.float32(9.0580006145e-06)
+
+
+def log1p_f32(x) -> np.ndarray:
+    """float32 log1p, restated from the public-domain fdlibm/musl ``log1pf`` (argument reduction of
+    1+x to [sqrt(2)/2, sqrt(2)) with the rounding error of 1+x carried as a correction term, degree-4
+    polynomial in s^2, s = f/(2+f); < 1 ulp).  Every operation is an individually rounded float32
+    op, so the CUDA kernels (csrc/common.cuh::log1p_f32) reproduce it bit for bit.  It agrees with
+    the correctly rounded log1p on ~94% of the erfinv domain and is within 1 ulp elsewhere -- the same
+    class of approximation XLA itself uses (XLA's log1p is not correctly rounded either).
+    Domain used here: -1 < x <= 0."""
+    f32, u32 = np.float32, np.uint32
+    x = np.asarray(x, f32)
+    ix = x.view(u32)
+    with np.errstate(all="ignore"):
+        small = (ix < u32(0x3ED413D0)) | ((ix >> u32(31)) == 1)          # 1 + x < sqrt(2)
+        tiny = small & ((ix << u32(1)) < u32(0x67000000))                # |x| < 2^-24: log1p(x) = x
+        k0 = small & (ix <= u32(0xBE95F619))                             # sqrt(2)/2 <= 1 + x: no reduction
+        u = (f32(1) + x).astype(f32)
+        iu = u.view(u32) + u32(0x3F800000 - 0x3F3504F3)
+        k = (iu >> u32(23)).astype(np.int32) - 0x7F
+        c = np.where(k >= 2, (f32(1) - (u - x).astype(f32)).astype(f32),
+                     (x - (u - f32(1)).astype(f32)).astype(f32)).astype(f32)
+        c = np.where(k < 25, (c / u).astype(f32), f32(0)).astype(f32)
+        f = (((iu & u32(0x007FFFFF)) + u32(0x3F3504F3)).view(f32) - f32(1)).astype(f32)
+        k = np.where(k0, 0, k)
+        c = np.where(k0, f32(0), c).astype(f32)
+        f = np.where(k0, x, f).astype(f32)
+        s = (f / (f32(2) + f).astype(f32)).astype(f32)
+        z = (s * s).astype(f32)
+        w = (z * z).astype(f32)
+        t1 = (w * (_LG2 + (w * _LG4).astype(f32)).astype(f32)).astype(f32)
+        t2 = (z * (_LG1 + (w * _LG3).astype(f32)).astype(f32)).astype(f32)
+        R = (t2 + t1).astype(f32)
+        hfsq = ((f32(0.5) * f).astype(f32) * f).astype(f32)
+        dk = k.astype(f32)
+        r = (s * (hfsq + R).astype(f32)).astype(f32)
+        r = (r + ((dk * _LN2_LO).astype(f32) + c).astype(f32)).astype(f32)
+        r = (r - hfsq).astype(f32)
+        r = (r + f).astype(f32)
+        r = (r + (dk * _LN2_HI).astype(f32)).astype(f32)
+    return np.where(tiny, x, r).astype(f32)
+
+
 def erfinv_f32(x) -> np.ndarray:
-    """XLA ``ErfInv32`` (Giles' single-precision polynomial).  ``log1p`` is evaluated in
-    float64 and rounded once, i.e. correctly rounded; every other op is a separately
-    rounded float32 op (no FMA contraction) -- the CUDA path does exactly the same, so
-    the two agree bit for bit; XLA:CPU's own log1p may differ from this by <= 1 ulp."""
+    """XLA ``ErfInv32`` (Giles' single-precision polynomial): w = -log1p(-x*x); two degree-8 Horner
+    branches; p*x.  ``log1p`` is ``log1p_f32`` above; every op is a separately rounded float32 op (no
+    FMA contraction) -- the CUDA path does exactly the same, so the two agree bit for bit; XLA:CPU's
+    own log1p may differ from this by <= 1 ulp."""
     x = np.asarray(x, dtype=np.float32)
     with np.errstate(divide="ignore", invalid="ignore"):
         t = (x * x).astype(np.float32)
-        w = (-np.log1p(-t.astype(np.float64))).astype(np.float32)
+        w = (-log1p_f32(-t)).astype(np.float32)
         lt = w < np.float32(5.0)
         w = np.where(lt, w - np.float32(2.5), np.sqrt(w) - np.float32(3.0)).astype(np.float32)
         p = np.where(lt, _ERFINV_LT5[0], _ERFINV_GE5[0]).astype(np.float32)
