@@ -29,6 +29,25 @@ class TargetDescriptor:
         d.X, d.y, d.vec0, d.vec1 = N.ptr(X), N.ptr(y), N.ptr(v0), N.ptr(v1)
         return d
 
+    def evaluate_metric(self, position):
+        """``jax.vmap(metric_fn)(position)``: (C, D) -> (C, D, D).  Built for the logistic-regression
+        target, where it runs as one tcgen05 (3xTF32) GEMM over the chain dimension."""
+        import ctypes as C
+        import torch
+        if self.kind != N.TARGET_LOGREG:
+            raise NotImplementedError("evaluate_metric() is built for the logistic-regression target")
+        q = position.to(torch.float32).contiguous()
+        if q.ndim != 2 or q.shape[1] != self.D:
+            raise ValueError(f"position must have shape (C, {self.D})")
+        d = self.c_struct()
+        ws_bytes = N.lib().gb200_logreg_fisher_metric_workspace(C.byref(d), q.shape[0])
+        ws = torch.empty(max(int(ws_bytes), 4) // 4, dtype=torch.float32, device=q.device)
+        G = torch.empty((q.shape[0], self.D, self.D), dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            N.check(N.lib().gb200_logreg_fisher_metric(C.byref(d), N.ptr(q), N.ptr(G), N.ptr(ws), ws_bytes,
+                                                       q.shape[0], N.F32, N.stream_ptr()))
+        return G
+
     def with_metric(self, metric: str) -> "TargetDescriptor":
         """``metric='identity'`` == ``metric_fn=lambda x: jnp.eye(D)`` (tests/test_samplers.py:25)."""
         m = {"target": N.METRIC_TARGET, "identity": N.METRIC_IDENTITY}[metric]

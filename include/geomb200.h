@@ -213,6 +213,15 @@ int gb200_ess_partial(const void* samples, int64_t T, int64_t C, int32_t D, int3
 int gb200_ess_finalize(const double* acov_host, const double* rhat_stats_host, int64_t T, int64_t C_total, int32_t D,
                        int32_t num_lags, double* ess_host, uint8_t* truncated_host);
 
+/* ---- batched metric evaluation: vmap(metric_fn)(position) -------------------------------------
+ * metric_fn of the logistic-regression target (the reference calls metric_fn at every kinetic-energy /
+ * velocity evaluation: rmhmc/metrics.py:46,62,121): G_c = X^T diag(s(1-s)) X + alpha I for every chain,
+ * computed as ONE tcgen05 (3xTF32) GEMM over the chain dimension.  position [C, D] -> metric [C, D, D].
+ * workspace: gb200_logreg_fisher_metric_workspace(target, C) bytes of device memory. */
+int gb200_logreg_fisher_metric(const gb200_target_desc* target, const void* position, void* metric, void* workspace,
+                               int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream);
+int64_t gb200_logreg_fisher_metric_workspace(const gb200_target_desc* target, int64_t C);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Runs a dependent-FMA microbenchmark (iters FFMA per thread on grid x block threads) for the FP32
  * roofline denominator; out[0] receives a checksum so the work cannot be elided. */

@@ -75,3 +75,20 @@ def test_logreg_fused_equals_stepwise_and_limits(cuda):
     big = g.logistic_regression(_t(Xb, cuda), _t(yb, cuda), 0.01)
     with pytest.raises(g._native.NativeError):
         g.rmhmc.init(torch.zeros((2, 30), device=cuda), big)
+
+
+@pytest.mark.parametrize("Nrows,D,C", [(1000, 25, 300), (64, 4, 7), (333, 17, 129), (2000, 32, 130)])
+def test_fisher_metric_tcgen05_vs_oracle(cuda, Nrows, D, C):
+    """vmap(metric_fn)(position) as one tcgen05 3xTF32 GEMM over the chain dimension vs the float64
+    oracle: error must stay at FP32 level (a single-pass TF32 product would be ~5e-4)."""
+    import geomjax_b200 as g
+    X, y = T.make_logreg_data(Nrows, D, seed=2)
+    t64 = T.LogisticRegression(X.astype(np.float64), y.astype(np.float64), 0.01, dtype=np.float64)
+    q = (0.3 * np.random.default_rng(C).standard_normal((C, D))).astype(np.float32)
+    want = t64.metric(q.astype(np.float64))
+    target = g.logistic_regression(_t(X, cuda), _t(y, cuda), 0.01)
+    got = target.evaluate_metric(_t(q, cuda)).cpu().numpy()
+    scale = np.abs(want).max(axis=(1, 2), keepdims=True)
+    err = np.abs(got - want) / scale
+    assert err.max() < 5e-6, err.max()  # FP32-level (two-level accumulation, see fisher_tc.cu)
+    np.testing.assert_array_equal(got, got.transpose(0, 2, 1))
