@@ -533,9 +533,23 @@ static int lr_setup(const gb200_target_desc& t, LogRegDev* tg, size_t* smem) {
   return GB200_OK;
 }
 
+int launch_rmhmc_logreg_tc(const TransArgs& a, const gb200_target_desc& t, cudaStream_t s);
+
 int launch_rmhmc_logreg(const TransArgs& a, const gb200_target_desc& t, int dtype, cudaStream_t s) {
   if (dtype != GB200_F32) { set_error("logreg: float32 only"); return GB200_ERR_UNSUPPORTED; }
   if (t.metric != GB200_METRIC_TARGET) { set_error("logreg: only the Fisher metric is built"); return GB200_ERR_UNSUPPORTED; }
+  if (!t.vec0 || !t.y || t.N < 1) { set_error("logreg: needs vec0 = X^T [D, ldx] (ldx = params[1]) and y [N]"); return GB200_ERR_INVALID_ARGUMENT; }
+  // Preferred path: lock-step tile kernel with both D^2 N products on tcgen05 (rmhmc_logreg_tc.cu).
+  // It needs a tile of chains to amortise the shared operand; tiny batches, per-chain step sizes and
+  // shapes outside its limits run on the CTA-per-chain FP32 kernel below.  GB200_LOGREG_TC=0 forces that.
+  {
+    static const char* env = getenv("GB200_LOGREG_TC");
+    const bool allow = !(env && env[0] == '0');
+    if (allow && a.C >= 32) {
+      const int rc = launch_rmhmc_logreg_tc(a, t, s);
+      if (rc != GB200_ERR_UNSUPPORTED) return rc;
+    }
+  }
   LogRegDev tg;
   size_t smem;
   int rc = lr_setup(t, &tg, &smem);

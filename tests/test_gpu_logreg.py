@@ -19,7 +19,8 @@ def _close(got, want, rtol, atol, what=""):
     np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, err_msg=what)
 
 
-@pytest.mark.parametrize("Nrows,D,C,L", [(40, 3, 9, 1), (200, 8, 20, 2), (1000, 25, 6, 1), (1000, 25, 4, 3), (333, 17, 5, 2)])
+@pytest.mark.parametrize("Nrows,D,C,L", [(40, 3, 9, 1), (200, 8, 20, 2), (1000, 25, 6, 1), (1000, 25, 4, 3), (333, 17, 5, 2),
+                                          (40, 3, 64, 1), (200, 8, 40, 2), (1000, 25, 70, 1), (1000, 25, 33, 2), (333, 17, 65, 2)])
 def test_rmhmc_logreg_vs_oracle(cuda, Nrows, D, C, L):
     import geomjax_b200 as g
     X, y = T.make_logreg_data(Nrows, D, seed=1)
