@@ -63,7 +63,8 @@ class KeySource(C.Structure):
 class RunOpts(C.Structure):
     _fields_ = [("samples", vp), ("sample_accept", vp), ("noise_override", vp), ("uniform_override", vp),
                 ("dual_averaging", vp), ("da_target", C.c_double), ("da_t0", C.c_double),
-                ("da_gamma", C.c_double), ("da_kappa", C.c_double)]
+                ("da_gamma", C.c_double), ("da_kappa", C.c_double),
+                ("workspace", vp), ("workspace_bytes", C.c_int64)]
 
 
 _i32, _i64, _dbl = C.c_int32, C.c_int64, C.c_double
@@ -71,6 +72,7 @@ _P = C.POINTER
 
 PROTOTYPES = {
     "gb200_version": (C.c_int, []),
+    "gb200_kernel_launches": (C.c_longlong, []),
     "gb200_last_error": (C.c_char_p, []),
     "gb200_threefry_split": (C.c_int, [vp, vp, _i64, _i32, _i32, vp]),
     "gb200_random_bits": (C.c_int, [vp, vp, _i64, _i32, _i32, vp]),

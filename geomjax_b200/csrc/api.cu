@@ -1,3 +1,4 @@
+#include <atomic>
 // C-ABI entry points (include/geomb200.h).  No torch types; plain pointers and sizes.
 #include <stdarg.h>
 #include <stdio.h>
@@ -14,6 +15,10 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------- PRNG test-surface kernels
 __global__ void k_split(const uint32_t* keys, uint32_t* out, long long n, int num, int mode) {
@@ -85,6 +90,7 @@ extern "C" {
 
 int gb200_version(void) { return GB200_VERSION; }
 const char* gb200_last_error(void) { return g_err; }
+long long gb200_kernel_launches(void) { return launches(); }
 
 int gb200_threefry_split(const uint32_t* keys, uint32_t* out, int64_t n, int32_t num, int32_t mode, void* stream) {
   if (!keys || !out || n < 0 || num <= 0) { set_error("threefry_split: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }

@@ -4,6 +4,7 @@
 
 namespace gb {
 void set_error(const char* fmt, ...);
+void count_launch();  // one kernel of this library enqueued (gb200_kernel_launches)
 #define GB_DECL_LPC(n)                                                                                              \
   int launch_lmcmonge_lpc##n(const TransArgs& a, const gb200_target_desc& t, LayoutChoice lay, int dtype, cudaStream_t s); \
   int launch_lmc_lpc##n(const TransArgs& a, const gb200_target_desc& t, LayoutChoice lay, int dtype, cudaStream_t s);      \
@@ -37,4 +38,5 @@ inline int launch_init(const gb200_target_desc& t, gb200_state st, long long C, 
       gb::set_error("CUDA launch failed: %s", cudaGetErrorString(e_));           \
       return GB200_ERR_CUDA;                                                     \
     }                                                                            \
+    gb::count_launch();                                                          \
   } while (0)

@@ -388,7 +388,9 @@ __global__ void __launch_bounds__(LR_BLOCK, 1) rmhmc_logreg_kernel(const TransAr
   const float tol = (float)a.fp_tol, div_tol = (float)a.fp_div_tol;
   const long long T = a.ks.keys ? 1 : a.ks.num_transitions;
 
-  for (long long chain = blockIdx.x; chain < a.C; chain += gridDim.x) {
+  const long long nwork = a.work_list ? (long long)*a.work_count : a.C;
+  for (long long widx = blockIdx.x; widx < nwork; widx += gridDim.x) {
+    const long long chain = a.work_list ? (long long)a.work_list[widx] : widx;
     for (long long it = 0; it < T; ++it) {
       const long long t = a.ks.first_transition + it;
       const float* spos = (const float*)(it == 0 ? a.in_pos : a.out_pos) + chain * D;
@@ -535,26 +537,13 @@ static int lr_setup(const gb200_target_desc& t, LogRegDev* tg, size_t* smem) {
 
 int launch_rmhmc_logreg_tc(const TransArgs& a, const gb200_target_desc& t, cudaStream_t s);
 
-int launch_rmhmc_logreg(const TransArgs& a, const gb200_target_desc& t, int dtype, cudaStream_t s) {
-  if (dtype != GB200_F32) { set_error("logreg: float32 only"); return GB200_ERR_UNSUPPORTED; }
-  if (t.metric != GB200_METRIC_TARGET) { set_error("logreg: only the Fisher metric is built"); return GB200_ERR_UNSUPPORTED; }
-  if (!t.vec0 || !t.y || t.N < 1) { set_error("logreg: needs vec0 = X^T [D, ldx] (ldx = params[1]) and y [N]"); return GB200_ERR_INVALID_ARGUMENT; }
-  // Preferred path: lock-step tile kernel with both D^2 N products on tcgen05 (rmhmc_logreg_tc.cu).
-  // It needs a tile of chains to amortise the shared operand; tiny batches, per-chain step sizes and
-  // shapes outside its limits run on the CTA-per-chain FP32 kernel below.  GB200_LOGREG_TC=0 forces that.
-  {
-    static const char* env = getenv("GB200_LOGREG_TC");
-    const bool allow = !(env && env[0] == '0');
-    if (allow && a.C >= 32) {
-      const int rc = launch_rmhmc_logreg_tc(a, t, s);
-      if (rc != GB200_ERR_UNSUPPORTED) return rc;
-    }
-  }
+// CTA-per-chain FP32 kernel over all chains (work_list == NULL) or over a device-side work list
+static int launch_lr_per_chain(const TransArgs& a, const gb200_target_desc& t, cudaStream_t s) {
   LogRegDev tg;
   size_t smem;
   int rc = lr_setup(t, &tg, &smem);
   if (rc) return rc;
-  const int grid = (int)(a.C < 148 ? a.C : 148);
+  const int grid = a.work_list ? 148 : (int)(a.C < 148 ? a.C : 148);  // list length is only known on the device
   const int dp = (tg.D + 3) / 4 * 4;
 #define GB_LR(DPV)                                                                                              \
   if (dp == DPV) {                                                                                              \
@@ -568,6 +557,52 @@ int launch_rmhmc_logreg(const TransArgs& a, const gb200_target_desc& t, int dtyp
 #undef GB_LR
   set_error("logreg: unsupported D");
   return GB200_ERR_UNSUPPORTED;
+}
+
+int launch_rmhmc_logreg(const TransArgs& a0, const gb200_target_desc& t, int dtype, cudaStream_t s) {
+  if (dtype != GB200_F32) { set_error("logreg: float32 only"); return GB200_ERR_UNSUPPORTED; }
+  if (t.metric != GB200_METRIC_TARGET) { set_error("logreg: only the Fisher metric is built"); return GB200_ERR_UNSUPPORTED; }
+  if (!t.vec0 || !t.y || t.N < 1) { set_error("logreg: needs vec0 = X^T [D, ldx] (ldx = params[1]) and y [N]"); return GB200_ERR_INVALID_ARGUMENT; }
+  TransArgs a = a0;
+  a.work_count = nullptr;
+  a.work_list = nullptr;
+  // Preferred path (needs gb200_run_opts.workspace): per transition,
+  //   1. the lock-step tile kernel (rmhmc_logreg_tc.cu): both D^2 N products on tcgen05, 64 chains per CTA;
+  //      chains whose fixed point needs more than `lock_cap` iterations (the heavy tail: float32 iterates
+  //      stalling just above tol = 1e-6 run to max_iters = 100) are frozen and appended to a work list
+  //      instead of holding their whole tile hostage (which is what a vmapped while_loop does);
+  //   2. the CTA-per-chain FP32 kernel re-runs exactly those chains from their (untouched) input state
+  //      with the same keys -- same semantics, results as if every chain had been run independently.
+  // Small batches, per-chain step sizes, fused dual averaging and shapes outside the tile kernel's limits
+  // run on the CTA-per-chain kernel only.  GB200_LOGREG_TC=0 forces that, GB200_LOGREG_LOCK_CAP sets the cap.
+  static const char* env = getenv("GB200_LOGREG_TC");
+  static const char* env_cap = getenv("GB200_LOGREG_LOCK_CAP");
+  const bool allow = !(env && env[0] == '0');
+  const long long T = a.ks.keys ? 1 : a.ks.num_transitions;
+  if (allow && a.C >= 32 && a.opts.workspace != nullptr && a.opts.workspace_bytes >= 4 * a.C + 16) {
+    for (long long it = 0; it < T; ++it) {
+      TransArgs c = a;
+      c.work_count = (int*)a.opts.workspace;
+      c.work_list = c.work_count + 4;
+      c.lock_cap = env_cap ? atoi(env_cap) : 8;
+      if (a.ks.keys == nullptr) {
+        c.ks.first_transition = a.ks.first_transition + it;
+        c.ks.num_transitions = 1;
+      }
+      if (it > 0) { c.in_pos = a.out_pos; c.in_logp = a.out_logp; c.in_grad = a.out_grad; c.in_vol = a.out_vol; }
+      if (a.opts.samples) c.opts.samples = (float*)a.opts.samples + it * a.C * (long long)a.D;
+      if (a.opts.sample_accept) c.opts.sample_accept = (float*)a.opts.sample_accept + it * a.C;
+      cudaMemsetAsync(c.work_count, 0, 16, s);
+      int rc = launch_rmhmc_logreg_tc(c, t, s);
+      if (rc == GB200_ERR_UNSUPPORTED && it == 0) goto per_chain;
+      if (rc) return rc;
+      rc = launch_lr_per_chain(c, t, s);
+      if (rc) return rc;
+    }
+    return GB200_OK;
+  }
+per_chain:
+  return launch_lr_per_chain(a, t, s);
 }
 
 int launch_init_logreg(const gb200_target_desc& t, gb200_state st, long long C, int dtype, cudaStream_t s) {

@@ -241,7 +241,16 @@ __device__ __noinline__ void tc_pass1(const LogRegTC& tg, TCSmem& sm, const floa
 // optional momentum draw p = L z, inverse (packed into Gs), w = G^-1 pv ---------------------------------
 template <int DP>
 __device__ __noinline__ void tc_factor(const LogRegTC& tg, TCSmem& sm, bool draw, const float* pv, float* wout) {
+  // Warp per chain.  Column / row broadcasts go through a per-warp shared-memory scratch and are read
+  // back as float4 (a first version used one shuffle per matrix element: ~1200 dependent
+  // shuffle->FMA pairs per chain, 30% of the kernel).  The scratch lives in the operand-tile region,
+  // which is idle during this phase.
+  constexpr int LD = DP;                      // row stride of the scratch matrices (DP % 4 == 0)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, D = tg.D;
+  float* scratch = (float*)sm.A_hi + warp * (DP * LD + 32);
+  float* Lm = scratch;                        // L, row-major
+  float* XT = scratch;                        // (L^-1)^T: XT[c][k] = X[k][c]; reuses L's storage once X is complete
+  float* colb = scratch + DP * LD;            // one column
   for (int c = warp; c < TC_CB; c += TC_THREADS / 32) {
     float* Gc = sm.Gs + (size_t)c * tg.PS;
     float row[DP];
@@ -260,11 +269,17 @@ __device__ __noinline__ void tc_factor(const LogRegTC& tg, TCSmem& sm, bool draw
       const float lik = (lane == k) ? lkk : row[k] * (1.f / lkk);
       row[k] = lik;
       if (lane == k) diag = lkk;
+      if (lane < DP) colb[lane] = lik;
+      __syncwarp();
 #pragma unroll
-      for (int j = k + 1; j < DP; ++j) {
-        const float ljk = __shfl_sync(0xffffffffu, lik, j);
-        if (lane >= j) row[j] = fmaf(-lik, ljk, row[j]);
+      for (int j4 = (k + 1) / 4; j4 < DP / 4; ++j4) {
+        const float4 cj = *(const float4*)(colb + 4 * j4);
+        if (4 * j4 + 0 > k && lane >= 4 * j4 + 0) row[4 * j4 + 0] = fmaf(-lik, cj.x, row[4 * j4 + 0]);
+        if (4 * j4 + 1 > k && lane >= 4 * j4 + 1) row[4 * j4 + 1] = fmaf(-lik, cj.y, row[4 * j4 + 1]);
+        if (4 * j4 + 2 > k && lane >= 4 * j4 + 2) row[4 * j4 + 2] = fmaf(-lik, cj.z, row[4 * j4 + 2]);
+        if (4 * j4 + 3 > k && lane >= 4 * j4 + 3) row[4 * j4 + 3] = fmaf(-lik, cj.w, row[4 * j4 + 3]);
       }
+      __syncwarp();
     }
     float ld = (lane < D) ? logf(diag) : 0.f;
 #pragma unroll
@@ -276,30 +291,57 @@ __device__ __noinline__ void tc_factor(const LogRegTC& tg, TCSmem& sm, bool draw
       for (int j = 0; j < DP; ++j) s = fmaf((j <= lane) ? row[j] : 0.f, (j < D) ? sm.z[c * TC_DS + j] : 0.f, s);
       if (lane < D) sm.p[c * TC_DS + lane] = s;
     }
-    // X = L^-1: lane = column, X[i] = entry (i, lane)
+    // L (lower, zeros above the diagonal) to the scratch, row-major
+    if (lane < DP) {
+#pragma unroll
+      for (int j4 = 0; j4 < DP / 4; ++j4) {
+        float4 v;
+        v.x = (4 * j4 + 0 <= lane) ? row[4 * j4 + 0] : 0.f;
+        v.y = (4 * j4 + 1 <= lane) ? row[4 * j4 + 1] : 0.f;
+        v.z = (4 * j4 + 2 <= lane) ? row[4 * j4 + 2] : 0.f;
+        v.w = (4 * j4 + 3 <= lane) ? row[4 * j4 + 3] : 0.f;
+        *(float4*)(Lm + lane * LD + 4 * j4) = v;
+      }
+    }
+    __syncwarp();
+    // X = L^-1 by forward substitution: lane = column, X[i] = entry (i, lane); row i of L is a broadcast read
     float X[DP];
     const float rdiag = 1.f / diag;
 #pragma unroll
     for (int i = 0; i < DP; ++i) {
-      float s = (i == lane) ? 1.f : 0.f;
+      float s0 = (i == lane) ? 1.f : 0.f, s1 = 0.f;
 #pragma unroll
-      for (int k = 0; k < i; ++k) {
-        const float lik = __shfl_sync(0xffffffffu, row[k], i);  // L[i][k]
-        if (lane <= k) s = fmaf(-lik, X[k], s);
+      for (int k4 = 0; k4 < (i + 3) / 4; ++k4) {
+        const float4 l4 = *(const float4*)(Lm + i * LD + 4 * k4);
+        if (4 * k4 + 0 < i) s0 = fmaf(-l4.x, X[4 * k4 + 0], s0);
+        if (4 * k4 + 1 < i) s1 = fmaf(-l4.y, X[4 * k4 + 1], s1);
+        if (4 * k4 + 2 < i) s0 = fmaf(-l4.z, X[4 * k4 + 2], s0);
+        if (4 * k4 + 3 < i) s1 = fmaf(-l4.w, X[4 * k4 + 3], s1);
       }
       const float ri = __shfl_sync(0xffffffffu, rdiag, i);
-      X[i] = (lane <= i) ? s * ri : 0.f;
+      X[i] = (lane <= i) ? (s0 + s1) * ri : 0.f;
     }
-    // Ginv[i][lane] = sum_k X_i[k] X_lane[k] for i <= lane; packed into Gs
+    // (L^-1)^T to the scratch: row c = column c of X
+    __syncwarp();
+    if (lane < DP) {
+#pragma unroll
+      for (int k4 = 0; k4 < DP / 4; ++k4)
+        *(float4*)(XT + lane * LD + 4 * k4) = make_float4(X[4 * k4], X[4 * k4 + 1], X[4 * k4 + 2], X[4 * k4 + 3]);
+    }
+    __syncwarp();
+    // Ginv[i][lane] = sum_k X[k][i] X[k][lane]; column i of X = row i of XT (broadcast float4 reads)
 #pragma unroll
     for (int i = 0; i < DP; ++i) {
-      float a = 0.f;
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int k = i; k < DP; ++k) {
-        const float xik = __shfl_sync(0xffffffffu, X[k], i);
-        a = fmaf(xik, X[k], a);
+      for (int k4 = i / 4; k4 < DP / 4; ++k4) {
+        const float4 x4 = *(const float4*)(XT + i * LD + 4 * k4);
+        a0 = fmaf(x4.x, X[4 * k4 + 0], a0);
+        a1 = fmaf(x4.y, X[4 * k4 + 1], a1);
+        a0 = fmaf(x4.z, X[4 * k4 + 2], a0);
+        a1 = fmaf(x4.w, X[4 * k4 + 3], a1);
       }
-      if (lane < D && i <= lane) Gc[tc_pair_index(D, i, lane)] = a;
+      if (lane < D && i <= lane) Gc[tc_pair_index(D, i, lane)] = a0 + a1;
     }
     __syncwarp();
     if (pv != nullptr) {  // w = Ginv pv
@@ -325,27 +367,30 @@ __device__ __noinline__ void tc_pass2(const LogRegTC& tg, TCSmem& sm, const floa
   const int NT = (N + 127) / 128, KP = tg.PS / TC_KT;
   const uint32_t a_hi_s = (uint32_t)__cvta_generic_to_shared(sm.A_hi), a_lo_s = (uint32_t)__cvta_generic_to_shared(sm.A_lo);
   const uint32_t b_hi_s = (uint32_t)__cvta_generic_to_shared(sm.B_hi), b_lo_s = (uint32_t)__cvta_generic_to_shared(sm.B_lo);
-  for (int kp = 0; kp < KP; ++kp) {
-    // B tile: [chain][pair kp*32 ..], off-diagonal pairs count twice in x^T Ginv x
-    for (int e = tid; e < TC_CB * TC_KT; e += TC_THREADS) {
-      const int cc = e / TC_KT, kk = e - cc * TC_KT;
-      const int pr = kp * TC_KT + kk;
-      float v = 0.f;
-      if (pr < tg.P) v = sm.Gs[(size_t)cc * tg.PS + pr] * (sm.pair_i[pr] == sm.pair_j[pr] ? 1.f : 2.f);
-      float hi, lo;
-      tc_split(v, hi, lo);
-      const int off = tc_off(cc, kk);
-      *(float*)(sm.B_hi + off) = hi;
-      *(float*)(sm.B_lo + off) = lo;
+  // data-row tile outermost: the X tile is staged from L2 once per 128 rows (it was re-staged for every
+  // (pair tile, row tile) before: 10% of all stall samples); the small B tile (64 chains x 32 pairs) is
+  // rebuilt from Gs in shared memory for every round instead.
+  for (int nt = 0; nt < NT; ++nt) {
+    const int n0 = nt * 128;
+    __syncthreads();  // previous users of xs are done
+    for (int e = tid; e < D * 128; e += TC_THREADS) {
+      const int i = e >> 7, r = e & 127;
+      sm.xs[e] = (n0 + r < N) ? tg.Xt[(size_t)i * tg.ldx + n0 + r] : 0.f;
     }
-    for (int nt = 0; nt < NT; ++nt) {
-      const int n0 = nt * 128;
-      __syncthreads();  // previous users of xs / A are done
-      for (int e = tid; e < D * 128; e += TC_THREADS) {
-        const int i = e >> 7, r = e & 127;
-        sm.xs[e] = (n0 + r < N) ? tg.Xt[(size_t)i * tg.ldx + n0 + r] : 0.f;
+    __syncthreads();
+    for (int kp = 0; kp < KP; ++kp) {
+      // B tile: [chain][pair kp*32 ..], off-diagonal pairs count twice in x^T Ginv x
+      for (int e = tid; e < TC_CB * TC_KT; e += TC_THREADS) {
+        const int cc = e / TC_KT, kk = e - cc * TC_KT;
+        const int pr = kp * TC_KT + kk;
+        float v = 0.f;
+        if (pr < tg.P) v = sm.Gs[(size_t)cc * tg.PS + pr] * (sm.pair_i[pr] == sm.pair_j[pr] ? 1.f : 2.f);
+        float hi, lo;
+        tc_split(v, hi, lo);
+        const int off = tc_off(cc, kk);
+        *(float*)(sm.B_hi + off) = hi;
+        *(float*)(sm.B_lo + off) = lo;
       }
-      __syncthreads();
       {
         const int row = tid & 127, kh = (tid >> 7) * 16;
 #pragma unroll
@@ -374,7 +419,7 @@ __device__ __noinline__ void tc_pass2(const LogRegTC& tg, TCSmem& sm, const floa
           tc_mma(td, tc_desc(a_lo_s + adv), tc_desc(b_hi_s + adv), 1u);
         }
       }
-      tc_commit_and_wait(sm);
+      tc_commit_and_wait(sm);  // operands are single-buffered
     }
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -523,7 +568,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rmhmc_logreg_tc_kernel(const Tr
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ int any_s;
-  __shared__ int iters_s[TC_CB], nfp_s[TC_CB], active_s[TC_CB];
+  __shared__ int iters_s[TC_CB], nfp_s[TC_CB], active_s[TC_CB], straggler_s[TC_CB];
   const int tid = threadIdx.x, warp = tid >> 5, D = tg.D;
   sm.mbar_a = (uint32_t)__cvta_generic_to_shared(&mbar);
   sm.phase = 0;
@@ -596,6 +641,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rmhmc_logreg_tc_kernel(const Tr
         for (int i = 0; i < D; ++i) pw = fmaf(sm.p[tid * TC_DS + i], sm.w[tid * TC_DS + i], pw);
         sm.H0[tid] = -slogp[chain] + 0.5f * pw + 0.5f * sm.logdet[tid] + 0.91893853320467274178f * (float)D;
         iters_s[tid] = 0;
+        straggler_s[tid] = 0;
       }
       if (a.info.momentum) {
         for (int e = tid; e < TC_CB * TC_DS; e += TC_THREADS) {
@@ -618,7 +664,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rmhmc_logreg_tc_kernel(const Tr
           __syncthreads();
           if (tid < TC_CB) {
             const float nr = sm.nrm[tid];
-            const int go = (nfp_s[tid] < a.fp_max_iters) && (nr < __int_as_float(0x7f800000)) && (nr < div_tol) && (nr > tol);
+            int go = (nfp_s[tid] < a.fp_max_iters) && (nr < __int_as_float(0x7f800000)) && (nr < div_tol) && (nr > tol);
+            if (go && nfp_s[tid] >= a.lock_cap) {  // heavy-tailed chain: freeze it here, re-run it chain by chain
+              straggler_s[tid] = 1;
+              go = 0;
+            }
             active_s[tid] = go;
             if (go) any_s = 1;
           }
@@ -656,7 +706,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rmhmc_logreg_tc_kernel(const Tr
       // end state: log-density, gradient, velocity, energy, accept
       tc_pass1<DP>(tg, sm, sm.q, true);
       tc_factor<DP>(tg, sm, false, sm.p, sm.w);
-      if (tid < TC_CB && c0 + tid < a.C) {
+      if (tid < TC_CB && c0 + tid < a.C && straggler_s[tid]) {
+        a.work_list[atomicAdd(a.work_count, 1)] = (int)(c0 + tid);
+      }
+      if (tid < TC_CB && c0 + tid < a.C && !straggler_s[tid]) {
         const long long chain = c0 + tid;
         float pw = 0.f;
         for (int i = 0; i < D; ++i) pw = fmaf(sm.p[tid * TC_DS + i], sm.w[tid * TC_DS + i], pw);
@@ -682,7 +735,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rmhmc_logreg_tc_kernel(const Tr
       __syncthreads();
       for (int e = tid; e < TC_CB * TC_DS; e += TC_THREADS) {
         const int cc = e / TC_DS, i = e - cc * TC_DS;
-        if (i < D && c0 + cc < a.C) {
+        if (i < D && c0 + cc < a.C && !straggler_s[cc]) {
           const long long o = (c0 + cc) * D + i;
           if (a.info.proposal_position) ((float*)a.info.proposal_position)[o] = sm.q[e];
           if (a.info.proposal_momentum) ((float*)a.info.proposal_momentum)[o] = -sm.p[e];
@@ -717,6 +770,7 @@ int launch_rmhmc_logreg_tc(const TransArgs& a, const gb200_target_desc& t, cudaS
   const int MT = (tg.P + 127) / 128, NT = (tg.N + 127) / 128;
   if (tg.D > 28 || tg.D < 2 || MT * TC_CB > 512 || NT * TC_CB > 512) return GB200_ERR_UNSUPPORTED;
   if (a.step_size_per_chain != nullptr || a.opts.dual_averaging != nullptr) return GB200_ERR_UNSUPPORTED;
+  if (a.work_list == nullptr || a.work_count == nullptr) return GB200_ERR_UNSUPPORTED;
   const size_t smem = tc_smem_bytes(tg.D, tg.PS);
   if (smem > 227 * 1024) return GB200_ERR_UNSUPPORTED;
   const long long ntiles = (a.C + TC_CB - 1) / TC_CB;

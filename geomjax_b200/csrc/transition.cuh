@@ -28,6 +28,11 @@ struct TransArgs {
   int metric;  // gb200_metric_kind
   int mode;    // gb200_threefry_mode
   long long C;
+  // logreg tcgen05 lock-step path: chains whose fixed point needs more than lock_cap iterations are
+  // appended to work_list and re-run chain by chain (rmhmc_logreg.cu) instead of stalling their tile
+  int* work_count;
+  int* work_list;
+  int lock_cap;
 };
 
 __device__ __forceinline__ U2 transition_key(const TransArgs& a, long long chain, long long t) {

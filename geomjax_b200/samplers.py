@@ -219,6 +219,13 @@ class _Engine:
                     new("fp_iters", (C_,), torch.int32)
         p, keep = self._params(q)
         desc = self.target.c_struct()
+        if self.target.kind == N.TARGET_LOGREG and self.sampler == N.RMHMC:
+            # device scratch for the straggler work list of the tcgen05 lock-step path
+            if opts is None:
+                opts = N.RunOpts()
+            ws = torch.empty(C_ + 4, dtype=torch.int32, device=dev)
+            keep.append(ws)
+            opts.workspace, opts.workspace_bytes = N.ptr(ws), ws.numel() * 4
         with torch.cuda.device(dev):
             N.check(N.lib().gb200_step(self.sampler, C.byref(p), C.byref(desc), C.byref(key_source), st_in, st_out,
                                        C.byref(info_c) if want_info else None,

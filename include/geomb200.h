@@ -152,9 +152,14 @@ typedef struct gb200_run_opts {
                                   (optimizers/dual_averaging.py:101-123); step size = exp(log_x) */
   double da_target;            /* target acceptance rate (adaptation/step_size_adaptation.py:103) */
   double da_t0, da_gamma, da_kappa; /* (10, 0.05, 0.75) */
+  void* workspace;             /* optional device scratch; >= 4*C + 16 bytes enables the tcgen05 lock-step path of
+                                  rmhmc on the logistic-regression target (straggler work list) */
+  int64_t workspace_bytes;
 } gb200_run_opts;
 
 int gb200_version(void);
+/* Number of CUDA kernels this library has enqueued in this process (monotonic; bench.py's gpu_launches). */
+long long gb200_kernel_launches(void);
 const char* gb200_last_error(void);
 
 /* ---- PRNG test surface: jax.random.split / bits / uniform / normal --------------------- */
