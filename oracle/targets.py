@@ -79,6 +79,26 @@ class NealFunnel:
         eye = np.eye(D, dtype=self.dtype)
         return np.stack([self.hvp(q, np.broadcast_to(eye[i], q.shape)) for i in range(D)], -1)
 
+    def dhessian(self, q):
+        """out[c, j, l, i] = d^3 logp / dq_j dq_l dq_i (what jacfwd(hessian) yields)."""
+        dt = self.dtype
+        q = np.asarray(q, dt)
+        C, D = q.shape
+        x = q[:, :-1]
+        e = np.exp(-q[:, -1])
+        T3 = np.zeros((C, D, D, D), dt)
+        k = np.arange(D - 1)
+        V = D - 1
+        # H_kk = -e, H_kv = x_k e, H_vv = -1/sigma^2 - e |x|^2 / 2
+        T3[:, k, k, V] = e[:, None]            # d_v H_kk
+        T3[:, k, V, k] = e[:, None]            # d_xk H_kv
+        T3[:, V, k, k] = e[:, None]
+        T3[:, k, V, V] = -(x * e[:, None])     # d_v H_kv
+        T3[:, V, k, V] = -(x * e[:, None])
+        T3[:, V, V, k] = -(x * e[:, None])     # d_xk H_vv
+        T3[:, V, V, V] = dt.type(0.5) * e * (x * x).sum(-1)
+        return T3
+
     # examples/funnel/main.py:41-50
     def inverse_jacobian(self, q):
         dt = self.dtype
@@ -289,3 +309,55 @@ class WithMetric:
 def identity_metric(target):
     D, dt = target.D, target.dtype
     return WithMetric(target, lambda q: np.broadcast_to(np.eye(D, dtype=dt), (q.shape[0], D, D)).copy())
+
+
+def softabs_metric(target, alpha=1e6):
+    """SoftAbs metric (Betancourt 2013): with H = -hessian(logp) = Q diag(lam) Q^T,
+    G = Q diag(f(lam)) Q^T, f(lam) = lam coth(alpha lam), f(0) = 1/alpha.  The derivative is what autodiff
+    through ``eigh`` computes (Daleckii-Krein): d_k G = Q (J o (Q^T d_k H Q)) Q^T with
+    J_ij = (f_i - f_j)/(lam_i - lam_j), J_ii = f'(lam_i) = coth(a lam) - a lam / sinh^2(a lam).
+    The eigen-decomposition runs in float64 and the results are rounded to the target dtype once
+    (the spec the CUDA closed form for D = 2 is held to).  NEW metric, not in the reference; needs
+    ``target.hessian`` and ``target.dhessian``."""
+    dt = target.dtype
+
+    def f_and_fp(lam):
+        x = alpha * lam
+        small = np.abs(x) < 1e-4
+        big = np.abs(x) > 30.0
+        xs = np.where(small | big, 1.0, x)
+        coth = np.where(big, np.sign(x), 1.0 / np.tanh(xs))
+        csch2 = np.where(big, 0.0, 1.0 / np.sinh(xs) ** 2)
+        # series near 0: x coth x = 1 + x^2/3, d/dlam = (2/3) alpha x
+        f = np.where(small, (1.0 + x * x / 3.0) / alpha, lam * coth)
+        fp = np.where(small, (2.0 / 3.0) * x, coth - x * csch2)
+        return f, fp
+
+    def eig(q):
+        H = -np.asarray(target.hessian(q), np.float64)
+        H = 0.5 * (H + H.transpose(0, 2, 1))
+        lam, Q = np.linalg.eigh(H)
+        return lam, Q
+
+    def metric(q):
+        lam, Q = eig(q)
+        f, _ = f_and_fp(lam)
+        return np.einsum("cij,cj,ckj->cik", Q, f, Q).astype(dt)
+
+    def dmetric(q):
+        lam, Q = eig(q)
+        f, fp = f_and_fp(lam)
+        dl = lam[:, :, None] - lam[:, None, :]
+        df = f[:, :, None] - f[:, None, :]
+        # near-degenerate pairs use the derivative at the mean eigenvalue
+        _, fpm = f_and_fp(0.5 * (lam[:, :, None] + lam[:, None, :]))
+        close = np.abs(dl) <= 1e-9 * np.maximum(np.abs(lam[:, :, None]), np.abs(lam[:, None, :])) + 1e-300
+        J = np.where(close, fpm, df / np.where(close, 1.0, dl))
+        dH = -np.asarray(target.dhessian(q), np.float64)          # [c, j, l, i]
+        M = np.einsum("cja,cjli,clb->cabi", Q, dH, Q)             # Q^T d_i H Q
+        return np.einsum("cja,cab,cabi,clb->cjli", Q, J, M, Q).astype(dt)
+
+    w = WithMetric(target, metric, dmetric)
+    w.name = "softabs_" + getattr(target, "name", "target")
+    w.softabs_alpha = float(alpha)
+    return w
