@@ -13,6 +13,18 @@ void count_launch();  // one kernel of this library enqueued (gb200_kernel_launc
 GB_DECL_LPC(1) GB_DECL_LPC(2) GB_DECL_LPC(4) GB_DECL_LPC(8) GB_DECL_LPC(32)
 #undef GB_DECL_LPC
 
+// A launch is "lean" when it carries no Info outputs, no overrides, no adaptation and runs legacy
+// threefry: the fused multi-transition launches of a sampling run.  Lean kernel instantiations
+// compile all of that out (the fused kernels are instruction-cache bound).
+inline bool lean_launch(const TransArgs& a) {
+  const gb200_info& f = a.info;
+  return a.mode == GB200_THREEFRY_LEGACY && a.opts.noise_override == nullptr && a.opts.uniform_override == nullptr &&
+         a.opts.dual_averaging == nullptr && a.step_size_per_chain == nullptr && !f.noise && !f.momentum &&
+         !f.acceptance_rate && !f.is_accepted && !f.is_divergent && !f.energy && !f.proposal_position &&
+         !f.proposal_velocity && !f.proposal_momentum && !f.proposal_logdensity && !f.proposal_logdensity_grad &&
+         !f.proposal_volume_adjustment && !f.proposal_weight && !f.initial_energy && !f.accept_uniform && !f.fp_iters;
+}
+
 int launch_rmhmc_logreg(const TransArgs& a, const gb200_target_desc& t, int dtype, cudaStream_t s);
 int launch_init_logreg(const gb200_target_desc& t, gb200_state st, long long C, int dtype, cudaStream_t s);
 

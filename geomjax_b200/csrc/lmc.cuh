@@ -141,7 +141,8 @@ struct IdentityMetric {
   }
 };
 
-template <typename R, class Target, class Metric, int EPL, int LPC, bool EXACT>
+// LEAN: see lmcmonge.cuh (no Info / overrides / adaptation, legacy threefry: compiled out).
+template <typename R, class Target, class Metric, int EPL, int LPC, bool EXACT, bool LEAN = false>
 __global__ void __launch_bounds__(128) lmc_kernel(const TransArgs a, const Target tg) {
   using LAY = Lay<EPL, LPC, EXACT>;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,11 +161,13 @@ __global__ void __launch_bounds__(128) lmc_kernel(const TransArgs a, const Targe
 
     R eps = (R)a.step_size;
     R* da = nullptr;
-    if (a.opts.dual_averaging != nullptr) {
-      da = (R*)a.opts.dual_averaging + chain * 5;
-      eps = exp(da[0]);
-    } else if (a.step_size_per_chain != nullptr) {
-      eps = ((const R*)a.step_size_per_chain)[chain];
+    if (!LEAN) {
+      if (a.opts.dual_averaging != nullptr) {
+        da = (R*)a.opts.dual_averaging + chain * 5;
+        eps = exp(da[0]);
+      } else if (a.step_size_per_chain != nullptr) {
+        eps = ((const R*)a.step_size_per_chain)[chain];
+      }
     }
 
     R q[EPL], g[EPL], u[EPL];
@@ -175,37 +178,42 @@ __global__ void __launch_bounds__(128) lmc_kernel(const TransArgs a, const Targe
 
     U2 key = transition_key(a, chain, t);
     U2 k_v, k_a;
-    split2(a.mode, key, k_v, k_a);
+    split2(LEAN ? GB200_THREEFRY_LEGACY : a.mode, key, k_v, k_a);
     typename Target::Ctx ctx = tg.prepare(lay, q);
     {
       R z[EPL];
-      draw_noise<R>(a, lay, k_v, chain, z);
+      draw_noise<R, LAY, LEAN>(a, lay, k_v, chain, z);
       Metric::draw(lay, tg, ctx, q, z, u);
-      if (active) store_vec(lay, a.info.noise, chain, z);
+      if (!LEAN && active) store_vec(lay, a.info.noise, chain, z);
     }
-    if (active) store_vec(lay, a.info.momentum, chain, u);  // LMCInfo.velocity
+    if (!LEAN && active) store_vec(lay, a.info.momentum, chain, u);  // LMCInfo.velocity
     const R H0 = -l0 + Metric::kinetic(lay, tg, ctx, q, u) - J0;  // lmc_energy lmcmc/metrics.py:209-221
     R J = J0, lp = l0;
 
-    for (int s = 0; s < a.num_steps; ++s) {  // one_step lmcmc/integrators.py:93-142
+    // one_step lmcmc/integrators.py:93-142 = half-step, position + gradient refresh, half-step; written
+    // as 2L half-steps so that the half-step body exists once in the instruction stream.
+    const int nh = 2 * a.num_steps;
+#pragma unroll 1
+    for (int h = 0; h < nh; ++h) {
       J += Metric::half_step(lay, tg, ctx, q, g, u, eps);
+      if (!(h & 1)) {
 #pragma unroll
-      for (int k = 0; k < EPL; ++k) q[k] = fma(eps, u[k], q[k]);
-      ctx = tg.prepare(lay, q);
-      lp = tg.logp(ctx);
-      tg.grad(lay, ctx, q, g);
-      J += Metric::half_step(lay, tg, ctx, q, g, u, eps);
+        for (int k = 0; k < EPL; ++k) q[k] = fma(eps, u[k], q[k]);
+        ctx = tg.prepare(lay, q);
+        lp = tg.logp(ctx);
+        tg.grad(lay, ctx, q, g);
+      }
     }
 
     const R H1 = -lp + Metric::kinetic(lay, tg, ctx, q, u) - J;  // even in u: flip afterwards
-    MH<R> mh = metropolis<R>(a, k_a, chain, H0, H1);
+    MH<R> mh = metropolis<R, LEAN>(a, k_a, chain, H0, H1);
 
-    if (a.info.proposal_momentum != nullptr) {
+    if (!LEAN && a.info.proposal_momentum != nullptr) {
       R pm[EPL];
       Metric::Gv(lay, tg, ctx, q, u, pm);
       if (active) store_vec(lay, a.info.proposal_momentum, chain, pm, R(-1));
     }
-    if (active) {
+    if (!LEAN && active) {
       store_vec(lay, a.info.proposal_position, chain, q);
       store_vec(lay, a.info.proposal_velocity, chain, u, R(-1));
       store_vec(lay, a.info.proposal_logdensity_grad, chain, g);
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(128) lmc_kernel(const TransArgs a, const Targe
         store_scalar<R>(a.out_logp, chain, lp);
         store_scalar<R>(a.out_vol, chain, J);
         if (a.opts.sample_accept != nullptr) ((R*)a.opts.sample_accept)[it * a.C + chain] = mh.p_accept;
-        if (da != nullptr)
+        if (!LEAN && da != nullptr)
           dual_averaging_update<R>(da, mh.p_accept, (R)a.opts.da_target, (R)a.opts.da_t0, (R)a.opts.da_gamma,
                                    (R)a.opts.da_kappa);
       }

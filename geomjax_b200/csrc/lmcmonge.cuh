@@ -136,9 +136,15 @@ __device__ __forceinline__ void monge_draw(const LAY& lay, R a2, MongeVecs<R, LA
   }
 }
 
-template <typename R, class Target, int EPL, int LPC, bool EXACT, bool UNIT>
+// HS >= 0: the half-step variant is a compile-time constant.  LEAN: the launch carries no Info
+// outputs, no overrides, no dual averaging / per-chain step size and runs legacy threefry (the
+// fused multi-transition launches of a sampling run): all of that code is compiled out.  Both exist
+// because the kernel is instruction-cache bound (ncu: 35% of stall samples are no_instruction when
+// the hot code exceeds the 32 KB L1.5 I-cache).
+template <typename R, class Target, int EPL, int LPC, bool EXACT, bool UNIT, int HS = -1, bool LEAN = false>
 __global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const Target tg) {
   using LAY = Lay<EPL, LPC, EXACT>;
+  const int half_step = HS >= 0 ? HS : a.half_step;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long chain = tid / LPC;
   const bool active = chain < a.C;
@@ -169,11 +175,13 @@ __global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const 
 
     R eps = (R)a.step_size;
     R* da = nullptr;
-    if (a.opts.dual_averaging != nullptr) {
-      da = (R*)a.opts.dual_averaging + chain * 5;
-      eps = exp(da[0]);
-    } else if (a.step_size_per_chain != nullptr) {
-      eps = ((const R*)a.step_size_per_chain)[chain];
+    if (!LEAN) {
+      if (a.opts.dual_averaging != nullptr) {
+        da = (R*)a.opts.dual_averaging + chain * 5;
+        eps = exp(da[0]);
+      } else if (a.step_size_per_chain != nullptr) {
+        eps = ((const R*)a.step_size_per_chain)[chain];
+      }
     }
 
     R q[EPL];
@@ -200,14 +208,14 @@ __global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const 
     }
     U2 key = transition_key(a, chain, t);
     U2 k_v, k_a;
-    split2(a.mode, key, k_v, k_a);
+    split2(LEAN ? GB200_THREEFRY_LEGACY : a.mode, key, k_v, k_a);
     {
       R z[EPL];
-      draw_noise<R>(a, lay, k_v, chain, z);
+      draw_noise<R, LAY, LEAN>(a, lay, k_v, chain, z);
       monge_draw<R, LAY, UNIT>(lay, a2, m, z);
-      if (active) store_vec(lay, a.info.noise, chain, z);
+      if (!LEAN && active) store_vec(lay, a.info.noise, chain, z);
     }
-    if (active) store_vec(lay, a.info.momentum, chain, m.v);  // LMCInfo.velocity = the initial draw
+    if (!LEAN && active) store_vec(lay, a.info.momentum, chain, m.v);  // LMCInfo.velocity = the initial draw
     typename Target::Ctx ctx = tg.prepare(lay, q);
     {
       R u[EPL];
@@ -224,46 +232,52 @@ __global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const 
     const R H0 = -l0 + monge_kinetic<R, EPL, LPC, UNIT>(a2, m, L, slm) - J0;  // lmcmonge_energy
     R lp = l0;
 
-    // ---- L integrator steps: lmcmonge/integrators.py:63-153
-    for (int s = 0; s < a.num_steps; ++s) {
-      monge_half_step<R, EPL, LPC, UNIT>(a.half_step, a2, m, J, L, sL, rs, eps);
+    // ---- L integrator steps: lmcmonge/integrators.py:63-153.  One step = half-step, position /
+    // gradient / HVP refresh, half-step, Hv refresh; written as 2L half-steps so that the half-step
+    // body exists once in the instruction stream (same operations in the same order).
+    const int nh = 2 * a.num_steps;
+#pragma unroll 1
+    for (int h = 0; h < nh; ++h) {
+      monge_half_step<R, EPL, LPC, UNIT>(half_step, a2, m, J, L, sL, rs, eps);
+      if (!(h & 1)) {
 #pragma unroll
-      for (int k = 0; k < EPL; ++k) q[k] = fma(eps, m.v[k], q[k]);
-      ctx = tg.prepare(lay, q);
-      lp = tg.logp(ctx);
-      tg.grad(lay, ctx, q, m.dl);  // un-normalised gradient for now
-      {
-        Acc4<R, EPL> sg;
+        for (int k = 0; k < EPL; ++k) q[k] = fma(eps, m.v[k], q[k]);
+        ctx = tg.prepare(lay, q);
+        lp = tg.logp(ctx);
+        tg.grad(lay, ctx, q, m.dl);  // un-normalised gradient for now
+        {
+          Acc4<R, EPL> sg;
 #pragma unroll
-        for (int k = 0; k < EPL; ++k) sg.fma(k, m.im(k) * m.dl[k], m.dl[k]);
-        L = R(1) + a2 * group_sum<LPC>(sg.total());
-      }
-      rs = fast_rsqrt(L);
-      sL = L * rs;
-      {
-        R u[EPL];
-#pragma unroll
-        for (int k = 0; k < EPL; ++k) {
-          m.dl[k] *= rs;
-          if (!UNIT) m.dl_ig_[UNIT ? 0 : k] = m.im(k) * m.dl[k];
-          u[k] = m.dl_ig(k);
+          for (int k = 0; k < EPL; ++k) sg.fma(k, m.im(k) * m.dl[k], m.dl[k]);
+          L = R(1) + a2 * group_sum<LPC>(sg.total());
         }
-        tg.hvp2(lay, ctx, q, u, m.v, rs, m.Hdl_ig, m.Hv);
-      }
-      if (!UNIT) {
+        rs = fast_rsqrt(L);
+        sL = L * rs;
+        {
+          R u[EPL];
 #pragma unroll
-        for (int k = 0; k < EPL; ++k) m.ig_Hdl_ig_[UNIT ? 0 : k] = m.im(k) * m.Hdl_ig[k];
+          for (int k = 0; k < EPL; ++k) {
+            m.dl[k] *= rs;
+            if (!UNIT) m.dl_ig_[UNIT ? 0 : k] = m.im(k) * m.dl[k];
+            u[k] = m.dl_ig(k);
+          }
+          tg.hvp2(lay, ctx, q, u, m.v, rs, m.Hdl_ig, m.Hv);
+        }
+        if (!UNIT) {
+#pragma unroll
+          for (int k = 0; k < EPL; ++k) m.ig_Hdl_ig_[UNIT ? 0 : k] = m.im(k) * m.Hdl_ig[k];
+        }
+      } else if (h + 1 < nh) {
+        tg.hvp(lay, ctx, q, m.v, rs, m.Hv);  // :132-134 (only feeds the next step)
       }
-      monge_half_step<R, EPL, LPC, UNIT>(a.half_step, a2, m, J, L, sL, rs, eps);
-      if (s + 1 < a.num_steps) tg.hvp(lay, ctx, q, m.v, rs, m.Hv);  // :132-134 (only feeds the next step)
     }
 
     // ---- flip, energy, accept: lmcmonge/lmc.py:512-534
     // energy is even in v, so evaluate on v and store -v
     const R H1 = -lp + monge_kinetic<R, EPL, LPC, UNIT>(a2, m, L, slm) - J;
-    MH<R> mh = metropolis<R>(a, k_a, chain, H0, H1);
+    MH<R> mh = metropolis<R, LEAN>(a, k_a, chain, H0, H1);
 
-    if (a.info.proposal_momentum != nullptr) {
+    if (!LEAN && a.info.proposal_momentum != nullptr) {
       // metric_vector_product with the un-normalised gradient g = dl * sL (integrators.py:136-138)
       R d = group_sum<LPC>(dotv<R, EPL>(m.v, m.dl)) * sL;
       const R c = a2 * L * d * sL;
@@ -275,7 +289,7 @@ __global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const 
     R gp[EPL];
 #pragma unroll
     for (int k = 0; k < EPL; ++k) gp[k] = m.dl[k] * sL;  // lmc.py:226-233
-    if (active) {
+    if (!LEAN && active) {
       store_vec(lay, a.info.proposal_position, chain, q);
       store_vec(lay, a.info.proposal_velocity, chain, m.v, R(-1));
       store_vec(lay, a.info.proposal_logdensity_grad, chain, gp);
@@ -310,7 +324,7 @@ __global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const 
         store_scalar<R>(a.out_logp, chain, lp);
         store_scalar<R>(a.out_vol, chain, J);
         if (a.opts.sample_accept != nullptr) ((R*)a.opts.sample_accept)[it * a.C + chain] = mh.p_accept;
-        if (da != nullptr)
+        if (!LEAN && da != nullptr)
           dual_averaging_update<R>(da, mh.p_accept, (R)a.opts.da_target, (R)a.opts.da_t0, (R)a.opts.da_gamma,
                                    (R)a.opts.da_kappa);
       }

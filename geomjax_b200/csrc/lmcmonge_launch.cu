@@ -9,6 +9,18 @@ static int launch_lmcmonge_t(const TransArgs& a, const Target& tg, LayoutChoice 
   launch_shape(a.C, lay.lpc, &grid, &block);
   const bool unit = a.inv_mass == nullptr;
   if constexpr (ALLOW_EXACT) {
+    // lean instantiations (no Info, no overrides, no adaptation, legacy threefry, unit mass)
+    const bool lean = unit && lean_launch(a);
+#define GB_XL(E, L, HSV)                                                                    \
+  if (lean && a.half_step == HSV && lay.epl == E && lay.lpc == L && a.D == E * L) {         \
+    lmcmonge_kernel<R, Target, E, L, true, true, HSV, true><<<grid, block, (size_t)block * lay.epl * sizeof(R), s>>>(a, tg); \
+    GB_CHECK_LAUNCH();                                                                      \
+    return GB200_OK;                                                                        \
+  }
+#define GB_XL3(E, L) GB_XL(E, L, GB200_HALF_STEP_OMEGA) GB_XL(E, L, GB200_HALF_STEP_OMEGA_FIXED) GB_XL(E, L, GB200_HALF_STEP_OMEGATILDE)
+    GB_MY_EXACT(GB_XL3)
+#undef GB_XL3
+#undef GB_XL
 #define GB_XE(E, L)                                                                         \
   if (lay.epl == E && lay.lpc == L && a.D == E * L) {                                       \
     if (unit) lmcmonge_kernel<R, Target, E, L, true, true><<<grid, block, (size_t)block * lay.epl * sizeof(R), s>>>(a, tg);   \

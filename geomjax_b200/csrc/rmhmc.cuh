@@ -137,7 +137,8 @@ __device__ __forceinline__ void midpoint_map(const LAY& lay, const Target& tg, c
   }
 }
 
-template <typename R, class Target, class Metric, int EPL, int LPC, bool EXACT>
+// LEAN: see lmcmonge.cuh (no Info / overrides / adaptation, legacy threefry: compiled out).
+template <typename R, class Target, class Metric, int EPL, int LPC, bool EXACT, bool LEAN = false>
 __global__ void __launch_bounds__(128) rmhmc_kernel(const TransArgs a, const Target tg) {
   using LAY = Lay<EPL, LPC, EXACT>;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,11 +157,13 @@ __global__ void __launch_bounds__(128) rmhmc_kernel(const TransArgs a, const Tar
 
     R eps = (R)a.step_size;
     R* da = nullptr;
-    if (a.opts.dual_averaging != nullptr) {
-      da = (R*)a.opts.dual_averaging + chain * 5;
-      eps = exp(da[0]);
-    } else if (a.step_size_per_chain != nullptr) {
-      eps = ((const R*)a.step_size_per_chain)[chain];
+    if (!LEAN) {
+      if (a.opts.dual_averaging != nullptr) {
+        da = (R*)a.opts.dual_averaging + chain * 5;
+        eps = exp(da[0]);
+      } else if (a.step_size_per_chain != nullptr) {
+        eps = ((const R*)a.step_size_per_chain)[chain];
+      }
     }
     const R he = R(0.5) * eps;
 
@@ -170,15 +173,15 @@ __global__ void __launch_bounds__(128) rmhmc_kernel(const TransArgs a, const Tar
 
     U2 key = transition_key(a, chain, t);
     U2 k_m, k_a;
-    split2(a.mode, key, k_m, k_a);
+    split2(LEAN ? GB200_THREEFRY_LEGACY : a.mode, key, k_m, k_a);
     typename Target::Ctx ctx = tg.prepare(lay, q);
     {
       R z[EPL];
-      draw_noise<R>(a, lay, k_m, chain, z);
+      draw_noise<R, LAY, LEAN>(a, lay, k_m, chain, z);
       Metric::draw(lay, tg, ctx, q, z, p);
-      if (active) store_vec(lay, a.info.noise, chain, z);
+      if (!LEAN && active) store_vec(lay, a.info.noise, chain, z);
     }
-    if (active) store_vec(lay, a.info.momentum, chain, p);  // RMHMCInfo.momentum
+    if (!LEAN && active) store_vec(lay, a.info.momentum, chain, p);  // RMHMCInfo.momentum
     const R H0 = -l0 + Metric::kinetic(lay, tg, ctx, q, p);  // hmc_energy
     int iters_total = 0;
 
@@ -235,14 +238,14 @@ __global__ void __launch_bounds__(128) rmhmc_kernel(const TransArgs a, const Tar
     R g[EPL];
     tg.grad(lay, ctx, q, g);
     const R H1 = -lp + Metric::kinetic(lay, tg, ctx, q, p);  // even in p
-    MH<R> mh = metropolis<R>(a, k_a, chain, H0, H1);
+    MH<R> mh = metropolis<R, LEAN>(a, k_a, chain, H0, H1);
 
-    if (a.info.proposal_velocity != nullptr) {
+    if (!LEAN && a.info.proposal_velocity != nullptr) {
       R w[EPL];
       Metric::Ginv(lay, tg, ctx, q, p, w);
       if (active) store_vec(lay, a.info.proposal_velocity, chain, w, R(-1));
     }
-    if (active) {
+    if (!LEAN && active) {
       store_vec(lay, a.info.proposal_position, chain, q);
       store_vec(lay, a.info.proposal_momentum, chain, p, R(-1));
       store_vec(lay, a.info.proposal_logdensity_grad, chain, g);
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(128) rmhmc_kernel(const TransArgs a, const Tar
       if (lay.g == 0) {
         store_scalar<R>(a.out_logp, chain, lout);
         if (a.opts.sample_accept != nullptr) ((R*)a.opts.sample_accept)[it * a.C + chain] = mh.p_accept;
-        if (da != nullptr)
+        if (!LEAN && da != nullptr)
           dual_averaging_update<R>(da, mh.p_accept, (R)a.opts.da_target, (R)a.opts.da_t0, (R)a.opts.da_gamma,
                                    (R)a.opts.da_kappa);
       }

@@ -53,11 +53,13 @@ __device__ __forceinline__ U2 transition_key(const TransArgs& a, long long chain
 // register array z[] is still filled with static indices.
 extern __shared__ unsigned char gb_smem[];
 
-template <typename R, class LAY>
+// LEAN: the launch has no noise override and runs legacy threefry (checked by the host), so only
+// one generation loop is compiled in (code size: the fused kernels are instruction-cache bound).
+template <typename R, class LAY, bool LEAN = false>
 __device__ __forceinline__ void draw_noise(const TransArgs& a, const LAY& lay, U2 key, long long chain,
                                            R (&z)[LAY::EPL]) {
   constexpr int EPL = LAY::EPL, LPC = LAY::LPC;
-  if (a.opts.noise_override != nullptr) {
+  if (!LEAN && a.opts.noise_override != nullptr) {
     const R* zo = (const R*)a.opts.noise_override + chain * a.D;
 #pragma unroll
     for (int k = 0; k < EPL; ++k) z[k] = lay.valid(k) ? zo[lay.j(k)] : R(0);
@@ -67,20 +69,22 @@ __device__ __forceinline__ void draw_noise(const TransArgs& a, const LAY& lay, U
   const int stride = blockDim.x;
   constexpr int DS = EPL * LPC;
   constexpr bool PAIRED = LAY::EXACT && (DS % 2 == 0) && ((DS / 2) % LPC == 0);
-  if (PAIRED && a.mode == GB200_THREEFRY_LEGACY) {
+  const int mode = LEAN ? GB200_THREEFRY_LEGACY : a.mode;
+  if (PAIRED && mode == GB200_THREEFRY_LEGACY) {
     constexpr int HK = EPL / 2;  // slots per half
 #pragma unroll 1
     for (int k = 0; k < HK; ++k) {  // 2 blocks = 4 normals in flight: threefry is a serial chain
       const uint32_t j = (uint32_t)lay.j(k);
       U2 o = threefry2x32(key.x, key.y, j, j + (uint32_t)(DS / 2));
-      zs[k * stride] = (R)bits_to_normal(o.x);
-      zs[(k + HK) * stride] = (R)bits_to_normal(o.y);
+      const float2 nz = bits_to_normal_x2(o.x, o.y);
+      zs[k * stride] = (R)nz.x;
+      zs[(k + HK) * stride] = (R)nz.y;
     }
   } else {
 #pragma unroll 1
     for (int k = 0; k < EPL; ++k) {  // 4 independent threefry + erfinv chains in flight (ILP)
       R v = R(0);
-      if (lay.valid(k)) v = (R)bits_to_normal(random_bits_elem(a.mode, key, (uint32_t)lay.j(k), (uint32_t)lay.D()));
+      if (lay.valid(k)) v = (R)bits_to_normal_call(random_bits_elem(mode, key, (uint32_t)lay.j(k), (uint32_t)lay.D()));
       zs[k * stride] = v;
     }
   }
@@ -95,7 +99,7 @@ struct MH {
   bool accept, divergent;
 };
 
-template <typename R>
+template <typename R, bool LEAN = false>
 __device__ __forceinline__ MH<R> metropolis(const TransArgs& a, U2 key_accept, long long chain, R H0, R H1) {
   MH<R> m;
   R delta = H0 - H1;
@@ -103,8 +107,8 @@ __device__ __forceinline__ MH<R> metropolis(const TransArgs& a, U2 key_accept, l
   m.weight = delta;
   m.p_accept = fmin(exp(delta), R(1));
   m.divergent = (-delta) > (R)a.divergence_threshold;
-  if (a.opts.uniform_override != nullptr) m.u = ((const R*)a.opts.uniform_override)[chain];
-  else m.u = (R)uniform_scalar(a.mode, key_accept);
+  if (!LEAN && a.opts.uniform_override != nullptr) m.u = ((const R*)a.opts.uniform_override)[chain];
+  else m.u = (R)uniform_scalar(LEAN ? GB200_THREEFRY_LEGACY : a.mode, key_accept);
   m.accept = m.u < m.p_accept;
   return m;
 }

@@ -171,3 +171,33 @@ def test_shipped_example_first_transition(cuda):
     onew, oinfo = S.lmc_step(S.chain_keys(P.key(0), 1000, 0, 8), ost, tgt, 0.1, 8)
     _close(st1.position, onew.position, rtol=1e-4)
     np.testing.assert_array_equal(info.is_accepted.cpu().numpy(), oinfo.is_accepted)
+
+
+@pytest.mark.parametrize("sampler,D", [("lmc", 100), ("lmc", 20), ("lmc", 2), ("rmhmc", 20), ("rmhmc", 2),
+                                       ("lmcmonge", 20), ("lmcmonge", 2), ("lmcmonge", 100)])
+def test_lean_fused_kernels_equal_stepwise(cuda, sampler, D):
+    """The lean instantiations (no Info / overrides / adaptation, compile-time half-step: what a fused
+    sampling launch runs) are bit-identical to T single steps through the full kernels."""
+    import torch
+    import geomjax_b200 as g
+    import geomjax_b200.random as R
+    C, T_ = 70, 4
+    target = g.neal_funnel(D)
+    if sampler == "lmc":
+        alg = g.lmc(target, 0.3 / np.sqrt(D), target, 3)
+    elif sampler == "rmhmc":
+        alg = g.rmhmc(target, 0.3 / np.sqrt(D), target, 3)
+    else:
+        alg = g.lmcmonge(target, 0.2 / np.sqrt(D), torch.ones(D, device=cuda), 3,
+                         integrator=g.integrators.half_step_omega_fixed)
+    root = P.key(3)
+    st0 = alg.init(torch.ones((C, D), device=cuda))
+    st, pos = st0, []
+    for t in range(T_):
+        st, info = alg.step(R.chain_keys(root, t, T_, C), st)
+        pos.append(st.position.clone())
+    fst, samples, _ = g.run_fused(alg.step, root, st0, T_, return_samples=True)
+    assert bool((samples == torch.stack(pos)).all())
+    for a_, b_ in zip(fst, st):
+        assert bool((a_ == b_).all())
+    assert float((samples[-1] != samples[0]).float().mean()) > 0.5  # chains actually moved
