@@ -12,6 +12,6 @@ from .samplers import (LMCInfo, LMCState, Proposal, RMHMCInfo, RMHMCState, lmc, 
                        run_fused)
 from .diagnostics import effective_sample_size as ess  # noqa: F401
 from .diagnostics import potential_scale_reduction as rhat  # noqa: F401
-from .targets import TargetDescriptor, banana, gaussian, logistic_regression, neal_funnel  # noqa: F401
+from .targets import TargetDescriptor, banana, gaussian, logistic_regression, neal_funnel, softabs  # noqa: F401
 
 __version__ = "0.1.0"

@@ -19,7 +19,7 @@ LEGACY, PARTITIONABLE = 0, 1
 RMHMC, LMC, LMCMONGE = 0, 1, 2
 HALF_STEP = {"omega": 0, "omega_fixed": 1, "omegatilde": 2}
 TARGET_FUNNEL, TARGET_GAUSSIAN, TARGET_BANANA, TARGET_LOGREG = 0, 1, 2, 3
-METRIC_TARGET, METRIC_IDENTITY = 0, 1
+METRIC_TARGET, METRIC_IDENTITY, METRIC_SOFTABS = 0, 1, 2
 
 vp = C.c_void_p
 

@@ -212,6 +212,10 @@ int gb200_step(int32_t sampler, const gb200_kernel_params* p, const gb200_target
     if (sampler != GB200_RMHMC) { set_error("logreg: only rmhmc (Fisher metric) is built in this version"); return GB200_ERR_UNSUPPORTED; }
     return launch_rmhmc_logreg(a, *target, p->dtype, (cudaStream_t)stream);
   }
+  if (target->metric == GB200_METRIC_SOFTABS && sampler != GB200_RMHMC) {
+    set_error("step: the SoftAbs metric is built for rmhmc only");
+    return GB200_ERR_UNSUPPORTED;
+  }
   LayoutChoice lay;
   if (!choose_layout(target->D, p->lanes_per_chain, C, &lay)) {
     set_error("step: no layout for D=%d lanes_per_chain=%d", target->D, p->lanes_per_chain);

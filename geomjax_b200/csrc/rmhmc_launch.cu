@@ -1,4 +1,7 @@
 #include "rmhmc.cuh"
+#if GB_LPC == 1
+#include "softabs.cuh"
+#endif
 #include "launch.h"
 
 namespace gb {
@@ -45,6 +48,21 @@ int GB_LPC_NAME(launch_rmhmc)(const TransArgs& a, const gb200_target_desc& t, La
   }
   switch (t.kind) {
     case GB200_TARGET_FUNNEL: {
+      if (t.metric == GB200_METRIC_SOFTABS) {
+#if GB_LPC == 1
+        if (t.D == 2 && lay.epl == 2) {
+          FunnelSA<float> sa;
+          sa.setup(t);
+          int grid, block;
+          launch_shape(a.C, 1, &grid, &block);
+          rmhmc_kernel<float, FunnelSA<float>, SoftAbs2H<float>, 2, 1, true><<<grid, block, (size_t)block * 2 * sizeof(float), s>>>(a, sa);
+          GB_CHECK_LAUNCH();
+          return GB200_OK;
+        }
+#endif
+        set_error("rmhmc: the SoftAbs metric is built for the D = 2 funnel with one lane per chain");
+        return GB200_ERR_UNSUPPORTED;
+      }
       Funnel<float> tg;
       tg.setup(t);
       if (t.metric == GB200_METRIC_IDENTITY)

@@ -343,7 +343,8 @@ def _merge_target(logdensity_fn, metric_fn):
     if isinstance(metric_fn, str):
         return t.with_metric(metric_fn)
     m = as_target(metric_fn)
-    if (m.kind, m.D, m.params) != (t.kind, t.D, t.params):
+    pad = lambda ps: tuple(ps) + (0.0,) * (7 - len(ps))
+    if (m.kind, m.D, pad(m.base_params)) != (t.kind, t.D, pad(t.base_params)):
         raise ValueError("metric_fn must be the metric of the same target descriptor (or 'identity')")
     return m
 

@@ -54,6 +54,11 @@ class TargetDescriptor:
         t = TargetDescriptor(self.kind, self.D, self.params, m, self.N, *self._keep, name=self.name)
         return t
 
+    @property
+    def base_params(self):
+        """Parameters of the log-density (params[7] is reserved for the metric: softabs alpha)."""
+        return tuple(self.params[:7])
+
     # the reference passes the same object's bound methods as logdensity_fn / metric_fn
     @property
     def logp(self):
@@ -74,6 +79,17 @@ def neal_funnel(D: int = 2, mean: float = 0.0, sigma: float = 3.0) -> TargetDesc
     if D < 2:
         raise ValueError("neal_funnel needs D >= 2")
     return TargetDescriptor(N.TARGET_FUNNEL, D, (sigma,), name="neal_funnel")
+
+
+def softabs(target: TargetDescriptor, alpha: float = 1e6) -> TargetDescriptor:
+    """NEW metric (the metric BASELINE.json configs[0] names for rmhmc): the SoftAbs
+    map of the Hessian, ``G = Q diag(lam coth(alpha lam)) Q^T`` with ``-hessian(logp) = Q diag(lam) Q^T``.
+    Use as ``metric_fn``: ``rmhmc(funnel, eps, softabs(funnel), L)``.  Built for Neal's funnel, D = 2."""
+    if target.kind != N.TARGET_FUNNEL or target.D != 2:
+        raise NotImplementedError("softabs() is built for neal_funnel(D=2)")
+    params = list(target.base_params) + [0.0] * (7 - len(target.base_params)) + [float(alpha)]
+    return TargetDescriptor(target.kind, target.D, params, N.METRIC_SOFTABS, target.N, *target._keep,
+                            name="softabs(" + target.name + ")")
 
 
 def gaussian(mean, precision_diag) -> TargetDescriptor:

@@ -61,7 +61,9 @@ typedef enum gb200_target_kind {
 
 typedef enum gb200_metric_kind {
   GB200_METRIC_TARGET = 0,   /* the target's own Riemannian metric */
-  GB200_METRIC_IDENTITY = 1  /* metric_fn = lambda x: eye(D) (tests/test_samplers.py:25,37) */
+  GB200_METRIC_IDENTITY = 1, /* metric_fn = lambda x: eye(D) (tests/test_samplers.py:25,37) */
+  GB200_METRIC_SOFTABS = 2   /* SoftAbs of the Hessian (Betancourt 2013), params[7] = softabs alpha; rmhmc, funnel D = 2
+                              * (the metric BASELINE.json configs[0] names; NEW, not in the reference) */
 } gb200_metric_kind;
 
 typedef struct gb200_target_desc {
