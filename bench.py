@@ -44,6 +44,8 @@ def _oracle_chunk(args):
         tgt = Tg.LogisticRegression(X, y, cfg["prior_precision"])
     else:
         tgt = Tg.NealFunnel(D, cfg.get("sigma", 3.0))
+        if cfg.get("metric") == "softabs":
+            tgt = Tg.softabs_metric(tgt, cfg["softabs_alpha"])
     root = P.key(cfg["root_key"])
     q0 = (np.ones if cfg["init_position"] == "ones" else np.zeros)((C, D), np.float32)
     idx = np.arange(chain_offset, chain_offset + C)
@@ -206,7 +208,8 @@ def run_ours(args, cfg):
         sampler_id = N.LMC
     else:
         eps = args.step_size or cfg["step_size"]
-        alg = g.rmhmc(target, eps, target, L, lanes_per_chain=args.lanes_per_chain)
+        metric = g.softabs(target, cfg["softabs_alpha"]) if cfg.get("metric") == "softabs" else target
+        alg = g.rmhmc(target, eps, metric, L, lanes_per_chain=args.lanes_per_chain)
         sampler_id = N.RMHMC
 
     def barrier():
@@ -265,29 +268,48 @@ def run_ours(args, cfg):
     value = total_chains * L * TPS * K / (dev_ms * 1e-3)
     accept_now = None
 
-    # ---- e2e arm: host buffers, H2D + init + fused transitions + D2H inside the timed region
+    # ---- e2e arm: host buffers, H2D + init + fused transitions + D2H inside the timed region.
+    # Steps are double-buffered over two CUDA streams so that step k's copies overlap step k+1's
+    # kernel; every step still uploads its inputs from pinned memory and reads its results on the host.
     host_q = init_fill((C, D)).pin_memory()
-    host_out = torch.empty((C, D)).pin_memory()
-    host_acc = torch.empty((TPS, C)).pin_memory()
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    host_out = [torch.empty((C, D)).pin_memory() for _ in streams]
+    host_acc = [torch.empty((TPS, C)).pin_memory() for _ in streams]
+    done = [torch.cuda.Event() for _ in streams]
 
-    def e2e_step(first):
-        q = host_q.to(dev, non_blocking=True)
-        st = alg.init(q)
-        s, _, acc = g.run_fused(alg.step, root, st, TPS, first=first, total=total_transitions,
-                                chain_offset=rank * C, total_chains=total_chains, return_accept=True)
-        host_out.copy_(s.position, non_blocking=True)
-        host_acc.copy_(acc, non_blocking=True)
-        torch.cuda.synchronize()
-        return float(host_acc.mean())
+    def e2e_enqueue(i, first):
+        with torch.cuda.stream(streams[i]):
+            q = host_q.to(dev, non_blocking=True)
+            st = alg.init(q)
+            s, _, acc = g.run_fused(alg.step, root, st, TPS, first=first, total=total_transitions,
+                                    chain_offset=rank * C, total_chains=total_chains, return_accept=True)
+            host_out[i].copy_(s.position, non_blocking=True)
+            host_acc[i].copy_(acc, non_blocking=True)
+            done[i].record(streams[i])
 
-    for _ in range(max(W, 1)):
-        e2e_step(0)
+    def e2e_collect(i):
+        done[i].synchronize()
+        return float(host_acc[i].mean())
+
+    def e2e_run(n):
+        acc = None
+        for k in range(n):
+            e2e_enqueue(k % 2, k * TPS)
+            if k > 0:
+                acc = e2e_collect((k - 1) % 2)
+        return e2e_collect((n - 1) % 2)
+
+    e2e_run(max(W, 2))
     barrier()
     t0 = time.perf_counter()
+    cur = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for k in range(K):
-        accept_now = e2e_step(k * TPS)
+    for st_ in streams:
+        st_.wait_stream(cur)
+    accept_now = e2e_run(K)
+    for st_ in streams:
+        cur.wait_stream(st_)
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -323,7 +345,9 @@ def run_ours(args, cfg):
         del samples
 
     if rank == 0:
-        flops_unit = N.lib().gb200_flops_per_chain_step(sampler_id, target.c_struct())
+        flops_step = N.lib().gb200_flops_per_chain_step(sampler_id, target.c_struct())
+        flops_transition = N.lib().gb200_flops_per_transition(sampler_id, target.c_struct())
+        flops_unit = flops_step + flops_transition / L   # per-transition work amortised over the L steps
         fp_iters_per_step = None
         if sampler_id == N.RMHMC:
             # implicit midpoint: (2 + iters) evaluations of the fixed-point map per step; measure iters
@@ -337,7 +361,7 @@ def run_ours(args, cfg):
                 feval = 2.0 * Nr * D * D + 10.0 * Nr * D + D ** 3
             else:
                 feval = 21.0 * D + 50.0
-            flops_unit = (2.0 + fp_iters_per_step) * feval
+            flops_unit = (2.0 + fp_iters_per_step) * feval + flops_transition / L
         med_ms = float(np.median(kernel_ms))
         ach = flops_unit * C * L * TPS / (med_ms * 1e-3) / 1e12
         peaks = {}
@@ -346,6 +370,13 @@ def run_ours(args, cfg):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tr.get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         state_bytes = (2 * (2 * D + 2) * 4) * C * TPS  # read + write of (q, grad, logp, vol) per transition
         line = {
             "metric": METRIC, "value": value, "unit": "chain-steps/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -359,14 +390,18 @@ def run_ours(args, cfg):
                                     "(compute-bound kernel; state re-read per transition is L1/L2 resident by design)",
                        "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
             "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                         "frac": ach / fp32_peak_tflops, "traffic": None,
-                         "flops_per_chain_step": flops_unit, "fp_iters_per_step": fp_iters_per_step, "kernel_ms_median": med_ms,
+                         "frac": ach / fp32_peak_tflops,
+                         "traffic": traffic,
+                         "flops_per_chain_step": flops_unit, "flops_per_integrator_step": flops_step,
+                         "flops_per_transition_outside_steps": flops_transition,
+                         "fp_iters_per_step": fp_iters_per_step, "kernel_ms_median": med_ms,
                          "peak_source": "measured in this process: FFMA microbenchmark kernel (148x8 CTAs x 256 thr, 8 independent FMA chains)",
                          "hbm": {"achieved_gbs": state_bytes / (med_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                                  "note": "state traffic only; HBM is not the bound"}},
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": C * D * 4,
-                    "d2h_bytes_per_step": C * D * 4 + TPS * C * 4, "mean_acceptance": accept_now},
+                    "d2h_bytes_per_step": C * D * 4 + TPS * C * 4, "mean_acceptance": accept_now,
+                    "pipelining": "2 CUDA streams, double-buffered pinned host buffers"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "wall_s": wall,

@@ -98,6 +98,7 @@ PROTOTYPES = {
     "gb200_logreg_fisher_metric_workspace": (_i64, [_P(TargetDesc), _i64]),
     "gb200_fp32_peak_kernel": (C.c_int, [vp, _i32, _i32, _i64, vp]),
     "gb200_flops_per_chain_step": (_dbl, [_i32, _P(TargetDesc)]),
+    "gb200_flops_per_transition": (_dbl, [_i32, _P(TargetDesc)]),
 }
 
 

@@ -237,4 +237,24 @@ double gb200_flops_per_chain_step(int32_t sampler, const gb200_target_desc* t) {
   return 0.0;
 }
 
+// Algorithmic FP32 flops per chain per TRANSITION outside the integrator steps (amortised over L by
+// the caller): the normal transform of D uniforms (u, u^2, log1p: 2 divisions + ~22, branch offset,
+// degree-8 Horner, scale: ~46 per normal), the draw, both energies and the sampler's prologue.
+// Integer threefry work (75 ops per block) is NOT counted.  Derivation in DESIGN.md section 4.
+double gb200_flops_per_transition(int32_t sampler, const gb200_target_desc* t) {
+  if (!t) return 0.0;
+  const double D = t->D;
+  if (t->kind == GB200_TARGET_FUNNEL) {
+    switch (sampler) {
+      // normals 46D; L + normalise 3D+3; two HVPs 10D+12; rank-one Cholesky draw 11D; two kinetic
+      // energies 8D+20; gradient rescale + accept D+5
+      case GB200_LMCMONGE: return 79.0 * D + 40.0;
+      // normals 46D; arrow-factor draw 4D; two kinetic energies 8D+20; accept ~10
+      case GB200_LMC: return 58.0 * D + 30.0;
+      case GB200_RMHMC: return 58.0 * D + 30.0;
+    }
+  }
+  return 0.0;
+}
+
 }  // extern "C"

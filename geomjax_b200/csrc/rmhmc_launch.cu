@@ -11,15 +11,9 @@ static int launch_rmhmc_t(const TransArgs& a, const Target& tg, LayoutChoice lay
   int grid, block;
   launch_shape(a.C, lay.lpc, &grid, &block);
   if constexpr (ALLOW_EXACT) {
-    const bool lean = lean_launch(a);
-#define GB_XL(E, L)                                                                   \
-  if (lean && lay.epl == E && lay.lpc == L && a.D == E * L) {                         \
-    rmhmc_kernel<R, Target, Metric, E, L, true, true><<<grid, block, (size_t)block * lay.epl * sizeof(R), s>>>(a, tg);  \
-    GB_CHECK_LAUNCH();                                                                \
-    return GB200_OK;                                                                  \
-  }
-    GB_MY_EXACT(GB_XL)
-#undef GB_XL
+    // No lean instantiations for rmhmc: ptxas contracts a few FMAs differently once the Info stores are
+    // gone (measured: fused != stepwise in the last bit), and bit-identity of fused and stepwise
+    // launches is part of the contract.  lmc / lmcmonge lean kernels are bit-identical (tested).
 #define GB_XE(E, L)                                                                   \
   if (lay.epl == E && lay.lpc == L && a.D == E * L) {                                 \
     rmhmc_kernel<R, Target, Metric, E, L, true><<<grid, block, (size_t)block * lay.epl * sizeof(R), s>>>(a, tg);          \

@@ -72,8 +72,19 @@ __device__ __forceinline__ void draw_noise(const TransArgs& a, const LAY& lay, U
   const int mode = LEAN ? GB200_THREEFRY_LEGACY : a.mode;
   if (PAIRED && mode == GB200_THREEFRY_LEGACY) {
     constexpr int HK = EPL / 2;  // slots per half
+    int k = 0;
 #pragma unroll 1
-    for (int k = 0; k < HK; ++k) {  // 2 blocks = 4 normals in flight: threefry is a serial chain
+    for (; k + 1 < HK; k += 2) {  // two blocks per call (interleaved rounds), four normals
+      const uint32_t j0 = (uint32_t)lay.j(k), j1 = (uint32_t)lay.j(k + 1);
+      const U4 o = threefry2x32_x2(key.x, key.y, j0, j0 + (uint32_t)(DS / 2), j1, j1 + (uint32_t)(DS / 2));
+      const float2 na = bits_to_normal_x2(o.a0, o.a1);
+      const float2 nb = bits_to_normal_x2(o.b0, o.b1);
+      zs[k * stride] = (R)na.x;
+      zs[(k + HK) * stride] = (R)na.y;
+      zs[(k + 1) * stride] = (R)nb.x;
+      zs[(k + 1 + HK) * stride] = (R)nb.y;
+    }
+    if (k < HK) {
       const uint32_t j = (uint32_t)lay.j(k);
       U2 o = threefry2x32(key.x, key.y, j, j + (uint32_t)(DS / 2));
       const float2 nz = bits_to_normal_x2(o.x, o.y);

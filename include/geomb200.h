@@ -235,6 +235,9 @@ int64_t gb200_logreg_fisher_metric_workspace(const gb200_target_desc* target, in
 int gb200_fp32_peak_kernel(float* out, int32_t grid, int32_t block, int64_t iters, void* stream);
 /* Algorithmic FP32 flop count per chain per integrator step used for roofline.achieved. */
 double gb200_flops_per_chain_step(int32_t sampler, const gb200_target_desc* target);
+/* Algorithmic FP32 flop count per chain per transition outside the integrator steps (normal transform,
+ * draw, energies, prologue); bench.py amortises it over num_integration_steps. */
+double gb200_flops_per_transition(int32_t sampler, const gb200_target_desc* target);
 
 #ifdef __cplusplus
 }

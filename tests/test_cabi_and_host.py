@@ -84,6 +84,8 @@ def test_flop_model_and_facade_errors():
     d = t.c_struct()
     assert lib.gb200_flops_per_chain_step(N.LMCMONGE, C.byref(d)) == 59 * 20 + 60
     assert lib.gb200_flops_per_chain_step(N.LMC, C.byref(d)) == 25 * 20 + 140
+    assert lib.gb200_flops_per_transition(N.LMCMONGE, C.byref(d)) == 79 * 20 + 40
+    assert lib.gb200_flops_per_transition(N.LMC, C.byref(d)) == 58 * 20 + 30
     with pytest.raises(ValueError):
         g.neal_funnel(1)
     with pytest.raises(NotImplementedError):
