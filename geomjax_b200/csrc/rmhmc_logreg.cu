@@ -536,6 +536,13 @@ static int lr_setup(const gb200_target_desc& t, LogRegDev* tg, size_t* smem) {
 }
 
 int launch_rmhmc_logreg_tc(const TransArgs& a, const gb200_target_desc& t, cudaStream_t s);
+// rmhmc_logreg_big.cu: D > 32 or a design matrix that does not fit shared memory (X streamed from L2)
+int launch_rmhmc_logreg_big(const TransArgs& a, const gb200_target_desc& t, cudaStream_t s);
+int launch_init_logreg_big(const gb200_target_desc& t, gb200_state st, long long C, cudaStream_t s);
+static bool lr_needs_big(const gb200_target_desc& t) {
+  const int ldx = (int)t.params[1];
+  return t.D > LR_DMAX || lr_smem_bytes(t.D, ldx) > 220 * 1024;
+}
 
 // CTA-per-chain FP32 kernel over all chains (work_list == NULL) or over a device-side work list
 static int launch_lr_per_chain(const TransArgs& a, const gb200_target_desc& t, cudaStream_t s) {
@@ -566,6 +573,7 @@ int launch_rmhmc_logreg(const TransArgs& a0, const gb200_target_desc& t, int dty
   TransArgs a = a0;
   a.work_count = nullptr;
   a.work_list = nullptr;
+  if (lr_needs_big(t)) return launch_rmhmc_logreg_big(a, t, s);
   // Preferred path (needs gb200_run_opts.workspace): per transition,
   //   1. the lock-step tile kernel (rmhmc_logreg_tc.cu): both D^2 N products on tcgen05, 64 chains per CTA;
   //      chains whose fixed point needs more than `lock_cap` iterations (the heavy tail: float32 iterates
@@ -607,6 +615,7 @@ per_chain:
 
 int launch_init_logreg(const gb200_target_desc& t, gb200_state st, long long C, int dtype, cudaStream_t s) {
   if (dtype != GB200_F32) { set_error("logreg: float32 only"); return GB200_ERR_UNSUPPORTED; }
+  if (t.vec0 && t.y && t.N >= 1 && lr_needs_big(t)) return launch_init_logreg_big(t, st, C, s);
   LogRegDev tg;
   size_t smem;
   int rc = lr_setup(t, &tg, &smem);

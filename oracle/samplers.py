@@ -137,11 +137,14 @@ def _rmhmc_kinetic_grad(target, q, p):
     dT/dp = G^-1 p;  dT/dq_i = 1/2 tr(G^-1 d_i G) - 1/2 (G^-1 p)^T d_i G (G^-1 p)."""
     dt = target.dtype
     G = target.metric(q)
-    dG = target.dmetric(q)
     v = _solve(G, p)
     Ginv = np.linalg.inv(G)
-    tr = np.einsum("cjl,cjli->ci", Ginv, dG)
-    quad = np.einsum("cj,cjli,cl->ci", v, dG, v)
+    if getattr(target, "structured_dmetric", False):
+        tr, quad = target.contract_dmetric(q, Ginv, v)   # same contractions, dG never materialised
+    else:
+        dG = target.dmetric(q)
+        tr = np.einsum("cjl,cjli->ci", Ginv, dG)
+        quad = np.einsum("cj,cjli,cl->ci", v, dG, v)
     return (dt.type(0.5) * tr - dt.type(0.5) * quad).astype(dt), v.astype(dt)
 
 

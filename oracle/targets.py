@@ -286,6 +286,24 @@ class LogisticRegression:
         return np.einsum("cn,nj,nl,ni->cjli", wp, self.X, self.X, self.X, optimize=True).astype(dt)
 
 
+def _logreg_contract_dmetric(self, q, Ginv, v):
+    """tr(G^-1 d_i G) and v^T d_i G v for all i without materialising dG (C, D, D, D): the same einsum
+    contractions as the dense path of oracle/samplers.py::_rmhmc_kinetic_grad, re-associated through
+    d_i G = X^T diag(w' x_.i) X.  Needed for D = 100, N = 10,000 (dG would be 4 MB per chain and N D^3
+    flops); equality with the dense path is tested at small sizes."""
+    dt = self.dtype
+    s = self._s(self._eta(q))
+    wp = s * (dt.type(1) - s) * (dt.type(1) - dt.type(2) * s)          # (C, N)
+    h = np.einsum("nj,cjl,nl->cn", self.X, Ginv.astype(dt), self.X, optimize=True)
+    u = np.einsum("nj,cj->cn", self.X, v.astype(dt))
+    tr = np.einsum("cn,ni->ci", wp * h, self.X)
+    quad = np.einsum("cn,ni->ci", wp * u * u, self.X)
+    return tr.astype(dt), quad.astype(dt)
+
+
+LogisticRegression.contract_dmetric = _logreg_contract_dmetric
+
+
 class WithMetric:
     """Wrap a target with a different ``metric_fn`` (e.g. ``lambda x: jnp.eye(2)`` of
     tests/test_samplers.py:25,37)."""

@@ -20,15 +20,18 @@ def _close(got, want, rtol, atol, what=""):
 
 
 @pytest.mark.parametrize("Nrows,D,C,L", [(40, 3, 9, 1), (200, 8, 20, 2), (1000, 25, 6, 1), (1000, 25, 4, 3), (333, 17, 5, 2),
-                                          (40, 3, 64, 1), (200, 8, 40, 2), (1000, 25, 70, 1), (1000, 25, 33, 2), (333, 17, 65, 2)])
+                                          (40, 3, 64, 1), (200, 8, 40, 2), (1000, 25, 70, 1), (1000, 25, 33, 2), (333, 17, 65, 2),
+                                          # rmhmc_logreg_big.cu: D > 32 or X larger than shared memory; last = c5's shape
+                                          (300, 40, 5, 2), (50, 33, 4, 1), (4000, 30, 3, 1), (10000, 100, 3, 1)])
 def test_rmhmc_logreg_vs_oracle(cuda, Nrows, D, C, L):
     import geomjax_b200 as g
     X, y = T.make_logreg_data(Nrows, D, seed=1)
     tgt = T.LogisticRegression(X, y, 0.01)
+    tgt.structured_dmetric = Nrows * D ** 3 > 1e9  # same contractions without the (C, D, D, D) tensor
     rng = np.random.default_rng(D)
     q = (0.1 * rng.standard_normal((C, D))).astype(np.float32)
     keys = rng.integers(0, 2 ** 32, size=(C, 2), dtype=np.uint64).astype(np.uint32)
-    eps = 0.1
+    eps = 0.1 if D <= 40 else 0.05
     ost = S.rmhmc_init(q, tgt)
     onew, oinfo = S.rmhmc_step(keys, ost, tgt, eps, L)
     target = g.logistic_regression(_t(X, cuda), _t(y, cuda), 0.01)
@@ -72,10 +75,10 @@ def test_logreg_fused_equals_stepwise_and_limits(cuda):
     # lmc / lmcmonge on logreg and designs that do not fit shared memory are refused loudly
     with pytest.raises(g._native.NativeError):
         g.lmc(target, 0.1, target, 2).step(g.random.chain_keys(root, 0, 3, 33), g.lmc.init(st0.position, target))
-    Xb, yb = T.make_logreg_data(4000, 30, seed=3)
+    Xb, yb = T.make_logreg_data(500, 125, seed=3)  # D > 124 is not built
     big = g.logistic_regression(_t(Xb, cuda), _t(yb, cuda), 0.01)
     with pytest.raises(g._native.NativeError):
-        g.rmhmc.init(torch.zeros((2, 30), device=cuda), big)
+        g.rmhmc.init(torch.zeros((2, 125), device=cuda), big)
 
 
 @pytest.mark.parametrize("Nrows,D,C", [(1000, 25, 300), (64, 4, 7), (333, 17, 129), (2000, 32, 130)])

@@ -40,3 +40,17 @@ def test_funnel_metric_closed_forms():
     A = f.inverse_jacobian(q)
     np.testing.assert_allclose(np.linalg.cholesky(G), A.transpose(0, 2, 1), atol=1e-12)
     np.testing.assert_allclose(np.linalg.slogdet(G)[1], -(5 - 1) * q[:, -1] - 2 * np.log(3.0), atol=1e-12)
+
+
+def test_logreg_structured_dmetric_contraction_equals_dense():
+    """The D = 100 / N = 10,000 oracle path contracts d_i G without materialising it; same numbers."""
+    from oracle import samplers as S
+    X, y = T.make_logreg_data(50, 6, dtype=np.float64)
+    t = T.LogisticRegression(X, y, dtype=np.float64)
+    rng = np.random.default_rng(2)
+    q, p = 0.4 * rng.standard_normal((3, 6)), rng.standard_normal((3, 6))
+    dense, v1 = S._rmhmc_kinetic_grad(t, q, p)
+    t.structured_dmetric = True
+    fast, v2 = S._rmhmc_kinetic_grad(t, q, p)
+    np.testing.assert_allclose(fast, dense, rtol=1e-11, atol=1e-13)
+    np.testing.assert_array_equal(v1, v2)
