@@ -42,6 +42,7 @@ def _oracle_chunk(args):
     if cfg["target"] == "logreg":
         X, y = Tg.make_logreg_data(cfg["N"], D, cfg.get("data_seed", 0))
         tgt = Tg.LogisticRegression(X, y, cfg["prior_precision"])
+        tgt.structured_dmetric = cfg["N"] * D ** 3 > 1e9  # same contractions without the (C, D, D, D) tensor
     else:
         tgt = Tg.NealFunnel(D, cfg.get("sigma", 3.0))
         if cfg.get("metric") == "softabs":

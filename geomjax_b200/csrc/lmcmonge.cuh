@@ -45,7 +45,7 @@ __device__ __forceinline__ void monge_half_step(int HS, R a2, MongeVecs<R, EPL, 
     }
     R r[2] = {r0.total(), r1.total()};
     group_sum_n<LPC>(r);
-    const R f = a2 * (r[0] + he * r[1]) / det1;
+    const R f = a2 * (r[0] + he * r[1]) * fast_rcp(det1);
 #pragma unroll
     for (int k = 0; k < EPL; ++k) m.v[k] -= f * m.dl_ig(k);
   } else {
@@ -71,7 +71,7 @@ __device__ __forceinline__ void monge_half_step(int HS, R a2, MongeVecs<R, EPL, 
       s3.fma(k, m.v[k], m.Hv[k]);
     }
     const R d3 = group_sum<LPC>(s3.total());
-    R f = he * d3 / det1;
+    R f = he * d3 * fast_rcp(det1);
     if (HS == GB200_HALF_STEP_OMEGA_FIXED) f *= a2;
 #pragma unroll
     for (int k = 0; k < EPL; ++k) m.v[k] -= f * m.dl_ig(k);
@@ -244,16 +244,26 @@ __global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const 
         for (int k = 0; k < EPL; ++k) q[k] = fma(eps, m.v[k], q[k]);
         ctx = tg.prepare(lay, q);
         lp = tg.logp(ctx);
-        tg.grad(lay, ctx, q, m.dl);  // un-normalised gradient for now
-        {
-          Acc4<R, EPL> sg;
+        if constexpr (UNIT && Target::kGradSqnorm) {
+          // unit mass: L = 1 + a2 |grad|^2 straight from the context, dl = grad / sqrt(L) in one pass
+          L = R(1) + a2 * tg.grad_sqnorm(ctx);
+          rs = fast_rsqrt(L);
+          sL = L * rs;
+          tg.grad_scaled(lay, ctx, q, rs, m.dl);
+          R u[EPL];
 #pragma unroll
-          for (int k = 0; k < EPL; ++k) sg.fma(k, m.im(k) * m.dl[k], m.dl[k]);
-          L = R(1) + a2 * group_sum<LPC>(sg.total());
-        }
-        rs = fast_rsqrt(L);
-        sL = L * rs;
-        {
+          for (int k = 0; k < EPL; ++k) u[k] = m.dl[k];
+          tg.hvp2(lay, ctx, q, u, m.v, rs, m.Hdl_ig, m.Hv);
+        } else {
+          tg.grad(lay, ctx, q, m.dl);  // un-normalised gradient for now
+          {
+            Acc4<R, EPL> sg;
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) sg.fma(k, m.im(k) * m.dl[k], m.dl[k]);
+            L = R(1) + a2 * group_sum<LPC>(sg.total());
+          }
+          rs = fast_rsqrt(L);
+          sL = L * rs;
           R u[EPL];
 #pragma unroll
           for (int k = 0; k < EPL; ++k) {

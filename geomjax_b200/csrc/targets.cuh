@@ -85,6 +85,22 @@ struct Funnel {
     return c0 - R(0.5) * c.v * c.v * inv_s2 - hdm1 * c.v - R(0.5) * c.e * c.S;
   }
 
+  // |grad|^2 from the context alone (sum_k (x_k e)^2 = e^2 S): saves the lmcmonge kernel one D-long
+  // accumulation and one group reduction per integrator step; grad_scaled = grad * s in one rounding.
+  static constexpr bool kGradSqnorm = true;
+  __device__ __forceinline__ R grad_sqnorm(const Ctx& c) const {
+    const R gv = -c.v * inv_s2 - hdm1 + R(0.5) * c.e * c.S;
+    return ::fma(c.e * c.e, c.S, gv * gv);
+  }
+  template <class LAY>
+  __device__ __forceinline__ void grad_scaled(const LAY& lay, const Ctx& c, const R (&q)[LAY::EPL], R s,
+                                              R (&g)[LAY::EPL]) const {
+    const R gv = (-c.v * inv_s2 - hdm1 + R(0.5) * c.e * c.S) * s;
+    const R me = -c.e * s;
+#pragma unroll
+    for (int k = 0; k < LAY::EPL; ++k) g[k] = lay.last(k) ? gv : q[k] * me;
+  }
+
   template <class LAY>
   __device__ __forceinline__ void grad(const LAY& lay, const Ctx& c, const R (&q)[LAY::EPL],
                                        R (&g)[LAY::EPL]) const {
@@ -157,6 +173,7 @@ struct GaussianDiag {
   const R* mean;
   const R* prec;
   struct Ctx { R quad; };
+  static constexpr bool kGradSqnorm = false;
 
   __host__ void setup(const gb200_target_desc& t) {
     mean = (const R*)t.vec0;
@@ -205,6 +222,7 @@ template <typename R>
 struct Banana {
   R s1, inv_s1, b;
   struct Ctx { R x1, x2, r; };
+  static constexpr bool kGradSqnorm = false;
 
   __host__ void setup(const gb200_target_desc& t) {
     s1 = (R)t.params[0];
