@@ -69,6 +69,7 @@ __device__ __forceinline__ void draw_noise(const TransArgs& a, const LAY& lay, U
   const int stride = blockDim.x;
   constexpr int DS = EPL * LPC;
   constexpr bool PAIRED = LAY::EXACT && (DS % 2 == 0) && ((DS / 2) % LPC == 0);
+  constexpr bool CROSS = LAY::EXACT && !PAIRED && LPC > 1 && (DS % 2 == 0) && ((DS / 2) % LPC == LPC / 2);
   const int mode = LEAN ? GB200_THREEFRY_LEGACY : a.mode;
   if (PAIRED && mode == GB200_THREEFRY_LEGACY) {
     constexpr int HK = EPL / 2;  // slots per half
@@ -90,6 +91,23 @@ __device__ __forceinline__ void draw_noise(const TransArgs& a, const LAY& lay, U
       const float2 nz = bits_to_normal_x2(o.x, o.y);
       zs[k * stride] = (R)nz.x;
       zs[(k + HK) * stride] = (R)nz.y;
+    }
+  } else if (CROSS && mode == GB200_THREEFRY_LEGACY) {
+    // D even but the two halves of a legacy counter pair (j, j + D/2) live in lanes g and g ^ (LPC/2):
+    // hash each pair once in the lane that owns j, hand the second word to the partner lane with one
+    // shuffle (c3: D = 100 over 4 lanes -> 50 threefry blocks per chain instead of 100).
+    constexpr int H = DS / 2;
+    constexpr int KH = (H + LPC - 1) / LPC;  // slots whose element index can be < H
+    const int gp = lay.g ^ (LPC / 2);
+    const int off = (H + gp - lay.g) / LPC;  // slot of element (partner's j) + H in this lane
+#pragma unroll 1
+    for (int k = 0; k < KH; ++k) {
+      const uint32_t j = (uint32_t)lay.j(k);
+      const U2 o = threefry2x32(key.x, key.y, j, j + (uint32_t)H);
+      const uint32_t y = __shfl_xor_sync(0xffffffffu, o.y, LPC / 2);
+      const float2 nz = bits_to_normal_x2(o.x, y);
+      if ((int)j < H) zs[k * stride] = (R)nz.x;
+      if (gp + LPC * k < H) zs[(k + off) * stride] = (R)nz.y;
     }
   } else {
 #pragma unroll 1

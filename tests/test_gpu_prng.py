@@ -69,3 +69,34 @@ def test_extreme_normal_tails(cuda):
     want = P.normal(keys, (2,))
     np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
     assert np.abs(want).max() > 4.0
+
+
+@pytest.mark.parametrize("sampler,D,lpc", [("lmc", 100, 4), ("lmc", 20, 4), ("lmc", 20, 2), ("lmc", 20, 1), ("lmc", 33, 32),
+                                           ("lmc", 7, 1), ("lmcmonge", 20, 2), ("rmhmc", 20, 4), ("lmc", 100, 8)])
+def test_in_kernel_noise_and_uniform_bit_exact(cuda, sampler, D, lpc):
+    """The z ~ normal(k_m, (D,)) and u ~ uniform(k_a) a fused transition actually uses (every noise-loop
+    variant: paired counters in one lane, pairs split across lanes, generic) == jax.random semantics."""
+    import torch
+    import geomjax_b200 as g
+    from geomjax_b200 import _native as N
+    from oracle import prng as P
+    C = 37
+    rng = np.random.default_rng(D * 7 + lpc)
+    keys = rng.integers(0, 2 ** 32, size=(C, 2), dtype=np.uint64).astype(np.uint32)
+    target = g.neal_funnel(D)
+    if sampler == "lmc":
+        alg = g.lmc(target, 0.01, target, 1, lanes_per_chain=lpc)
+    elif sampler == "rmhmc":
+        alg = g.rmhmc(target, 0.01, target, 1, lanes_per_chain=lpc)
+    else:
+        alg = g.lmcmonge(target, 0.001, torch.ones(D, device=cuda), 1, lanes_per_chain=lpc)
+    st = alg.init(0.1 * torch.ones((C, D), device=cuda))
+    ks = N.KeySource()
+    kt = torch.from_numpy(keys).to(cuda)
+    ks.keys, ks.num_transitions = N.ptr(kt), 1
+    _, info = alg.step.engine.launch(st, ks, want_info=True, extra_info=True)
+    km, ka = P.split(keys, 2)[:, 0], P.split(keys, 2)[:, 1]
+    z = np.stack([P.normal(km[c], (D,)) for c in range(C)])
+    u = np.array([P.uniform(ka[c]) for c in range(C)], np.float32)
+    np.testing.assert_array_equal(info["noise"].cpu().numpy(), z)
+    np.testing.assert_array_equal(info["accept_uniform"].cpu().numpy(), u)
