@@ -21,7 +21,7 @@ constexpr int BG_TN = 128;   // data rows per tile
 constexpr int BG_LD = 132;   // row stride (floats) of the tile and metric buffers: 16-byte aligned rows
 constexpr int BG_ROWS = 128; // rows of both buffers
 constexpr int BG_DMAX = 124;
-constexpr int BG_NV = 13;    // small vectors of 128 floats
+constexpr int BG_NV = 18;    // small vectors of 128 floats
 
 struct BigLR {
   const float* Xt;  // [D, ldx]
@@ -38,7 +38,7 @@ struct BGSmem {
   unsigned char *tbi, *tbj;  // SYRK tile -> (bi, bj)
   __device__ float* v(int i) const { return vec + i * 128; }
 };
-enum { B_Q = 0, B_P, B_Q0, B_P0, B_QN, B_PN, B_G, B_W, B_DT, B_Z, B_RT, B_SW, B_HB };
+enum { B_Q = 0, B_P, B_Q0, B_P0, B_QN, B_PN, B_G, B_W, B_DT, B_Z, B_RT, B_SW, B_HB, B_COL, B_PART /* 4 vectors */ };
 
 __device__ __forceinline__ float bg_block_sum(float v, float* red) {
 #pragma unroll
@@ -69,6 +69,21 @@ __device__ __forceinline__ void bg_load_tile(const BigLR& tg, const BGSmem& sm, 
     }
     *(float4*)(sm.T + i * BG_LD + 4 * c4) = v;
   }
+}
+
+// out[c] = sum_i T[i][c] * vec[i] for the 128 data rows of the tile, all 512 threads (4 interleaved
+// partial sums per row, combined through shared memory).  Ends with the partials published: the caller
+// reads bg_tile_dot_result(sm, c) after the __syncthreads() inside.
+__device__ __forceinline__ void bg_tile_dot(const BigLR& tg, const BGSmem& sm, const float* vec) {
+  const int c = threadIdx.x & (BG_TN - 1), part = threadIdx.x >> 7;
+  float a = 0.f;
+  for (int i = part; i < tg.D; i += 4) a = fmaf(sm.T[i * BG_LD + c], vec[i], a);
+  sm.v(B_PART)[part * 128 + c] = a;
+  __syncthreads();
+}
+__device__ __forceinline__ float bg_tile_dot_result(const BGSmem& sm, int c) {
+  const float* pp = sm.v(B_PART);
+  return (pp[c] + pp[128 + c]) + (pp[256 + c] + pp[384 + c]);
 }
 
 // sum over the tile's rows of T[i][c] * s[c] for the features owned by this warp (i = warp + 16 k), added to acc[k]
@@ -107,10 +122,10 @@ __device__ float bg_pass_a(const BigLR& tg, const BGSmem& sm, const float* qv, f
   for (int n0 = 0; n0 < N; n0 += BG_TN) {
     bg_load_tile(tg, sm, n0);
     __syncthreads();
+    bg_tile_dot(tg, sm, qv);
     if (tid < BG_TN) {
       const int n = n0 + tid;
-      float eta = 0.f;
-      for (int i = 0; i < D; ++i) eta = fmaf(sm.T[i * BG_LD + tid], qv[i], eta);
+      const float eta = bg_tile_dot_result(sm, tid);
       float r = 0.f, s_w = 0.f;
       if (n < N) {
         const float yn = __ldg(tg.y + n);
@@ -196,17 +211,22 @@ __device__ float bg_pass_a(const BigLR& tg, const BGSmem& sm, const float* qv, f
 // like jnp.linalg.cholesky)
 __device__ float bg_cholesky(const BigLR& tg, const BGSmem& sm, float* red) {
   const int D = tg.D, tid = threadIdx.x;
+  float* col = sm.v(B_COL);
+  const int warp = tid >> 5, lane = tid & 31;
   for (int k = 0; k < D; ++k) {
     const float lkk = sqrtf(sm.G[k * BG_LD + k]);
     const float rk = 1.f / lkk;
     __syncthreads();
     if (tid == 0) sm.G[k * BG_LD + k] = lkk;
-    for (int i = k + 1 + tid; i < D; i += BG_THREADS) sm.G[i * BG_LD + k] *= rk;
+    for (int i = k + 1 + tid; i < D; i += BG_THREADS) {
+      const float l = sm.G[i * BG_LD + k] * rk;
+      sm.G[i * BG_LD + k] = l;
+      col[i] = l;  // contiguous copy of column k: the trailing update reads it conflict-free
+    }
     __syncthreads();
-    const int m = D - k - 1;
-    for (int idx = tid; idx < m * m; idx += BG_THREADS) {
-      const int i = k + 1 + idx / m, j = k + 1 + idx % m;
-      if (j <= i) sm.G[i * BG_LD + j] = fmaf(-sm.G[i * BG_LD + k], sm.G[j * BG_LD + k], sm.G[i * BG_LD + j]);
+    for (int i = k + 1 + warp; i < D; i += BG_THREADS / 32) {  // warp = row, lanes = columns k+1..i
+      const float lik = col[i];
+      for (int j = k + 1 + lane; j <= i; j += 32) sm.G[i * BG_LD + j] = fmaf(-lik, col[j], sm.G[i * BG_LD + j]);
     }
     __syncthreads();
   }
@@ -266,11 +286,8 @@ __device__ void bg_pass_b(const BigLR& tg, const BGSmem& sm, const float* w, flo
     bg_load_tile(tg, sm, n0);
     if (tid < BG_TN) hb[tid] = 0.f;
     __syncthreads();
-    if (tid < BG_TN) {
-      float u = 0.f;
-      for (int i = 0; i < D; ++i) u = fmaf(sm.T[i * BG_LD + tid], w[i], u);
-      ub[tid] = u;
-    }
+    bg_tile_dot(tg, sm, w);
+    if (tid < BG_TN) ub[tid] = bg_tile_dot_result(sm, tid);
     {
       // warp = group of 8 metric rows i0..i0+7, lane = 4 consecutive data rows
       const int i0 = 8 * warp;
