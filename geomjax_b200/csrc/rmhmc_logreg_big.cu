@@ -429,7 +429,16 @@ __global__ void __launch_bounds__(BG_THREADS, 1) rmhmc_logreg_big_kernel(const T
   float *g = sm.v(B_G), *w = sm.v(B_W), *z = sm.v(B_Z);
   const float tol = (float)a.fp_tol, div_tol = (float)a.fp_div_tol;
   const long long T = a.ks.keys ? 1 : a.ks.num_transitions;
-  for (long long chain = blockIdx.x; chain < a.C; chain += gridDim.x) {
+  // chains are handed out dynamically when the caller gave a workspace (gb200_run_opts.workspace): the
+  // fixed-point iteration count is heavy-tailed (a float32 iterate stalling just above tol runs to
+  // max_iters), and a static chain -> CTA map leaves most SMs idle behind the slowest CTA
+  __shared__ long long chain_s;
+  for (long long round = 0;; ++round) {
+    if (tid == 0) chain_s = a.work_count ? (long long)atomicAdd(a.work_count, 1) : (long long)blockIdx.x + round * gridDim.x;
+    __syncthreads();
+    const long long chain = chain_s;
+    __syncthreads();
+    if (chain >= a.C) break;
     for (long long it = 0; it < T; ++it) {
       const long long t = a.ks.first_transition + it;
       const float* spos = (const float*)(it == 0 ? a.in_pos : a.out_pos) + chain * D;
@@ -584,7 +593,14 @@ int launch_rmhmc_logreg_big(const TransArgs& a, const gb200_target_desc& t, cuda
   cudaError_t e = cudaFuncSetAttribute(rmhmc_logreg_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("logreg_big: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
   const int grid = (int)(a.C < 148 ? a.C : 148);
-  rmhmc_logreg_big_kernel<<<grid, BG_THREADS, smem, s>>>(a, tg);
+  TransArgs c = a;
+  c.work_count = nullptr;
+  c.work_list = nullptr;
+  if (a.opts.workspace != nullptr && a.opts.workspace_bytes >= 16) {
+    c.work_count = (int*)a.opts.workspace;
+    cudaMemsetAsync(c.work_count, 0, 16, s);
+  }
+  rmhmc_logreg_big_kernel<<<grid, BG_THREADS, smem, s>>>(c, tg);
   GB_CHECK_LAUNCH();
   return GB200_OK;
 }

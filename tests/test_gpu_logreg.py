@@ -96,3 +96,33 @@ def test_fisher_metric_tcgen05_vs_oracle(cuda, Nrows, D, C):
     err = np.abs(got - want) / scale
     assert err.max() < 5e-6, err.max()  # FP32-level (two-level accumulation, see fisher_tc.cu)
     np.testing.assert_array_equal(got, got.transpose(0, 2, 1))
+
+
+@pytest.mark.parametrize("Nrows,D", [(150, 6), (200, 40)])
+def test_step_size_adaptation_on_logreg(cuda, Nrows, D):
+    """c5's warm-up: vmapped dual averaging fused into the rmhmc logistic-regression kernels (per-chain step
+    size from the dual-averaging state, update in the kernel epilogue); D = 40 runs rmhmc_logreg_big.cu."""
+    import torch
+    import geomjax_b200 as g
+    X, y = T.make_logreg_data(Nrows, D, seed=4)
+    target = g.logistic_regression(_t(X, cuda), _t(y, cuda), 0.01)
+    C, W = 12, 40
+    res, info = g.step_size_adaptation(g.rmhmc, target, initial_step_size=0.5, metric_fn=target,
+                                       num_integration_steps=2).run(g.random.PRNGKey(2), torch.zeros((C, D), device=cuda), W)
+    eps = res.parameters["step_size"]
+    assert eps.shape == (C,) and bool(torch.isfinite(eps).all()) and bool((eps >= 1e-3).all())
+    assert float(eps.std()) > 0  # per-chain adaptation
+    acc = info["acceptance_rate"]
+    assert acc.shape == (W, C) and 0.5 < float(acc[-15:].mean()) <= 1.0
+    # first transition against the oracle (same keys: split(key_c, W)[0], step size 0.5)
+    import geomjax_b200.random as R
+    from oracle import prng as P
+    keys = P.split(P.split(P.key(2), C), W)[:, 0]
+    tgt = T.LogisticRegression(X, y, 0.01)
+    _, oi = S.rmhmc_step(keys, S.rmhmc_init(np.zeros((C, D), np.float32), tgt), tgt, 0.5, 2)
+    ok = oi.extra["fp_iters"] < 100
+    np.testing.assert_allclose(acc[0].cpu().numpy()[ok], oi.acceptance_rate[ok], rtol=0, atol=5e-3)
+    # adapted parameters plug back into the sampler
+    alg = g.rmhmc(target, eps, target, 2)
+    st, i2 = alg.step(g.random.chain_keys(g.random.PRNGKey(9), 0, 1, C), res.state)
+    assert bool(torch.isfinite(st.position).all())
