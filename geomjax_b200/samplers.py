@@ -189,11 +189,11 @@ class _Engine:
         q = _check_position(state[0], self.target)
         C_, D = q.shape
         dev, dt = q.device, q.dtype
-        fields = [q] + [t.contiguous() for t in state[1:]]
+        fields = [q] + [t.contiguous() for t in state[1:] if t is not None]  # rmhmc carries no volume_adjustment
         if out_state is None:
             out = [torch.empty_like(t) for t in fields]
         else:
-            out = list(out_state)
+            out = [t for t in out_state if t is not None]
         if not self.with_volume:
             fields = fields[:3] + [None]
             out = out[:3] + [None]
