@@ -140,7 +140,7 @@ int gb200_init(const gb200_target_desc* target, gb200_state st, int64_t C, int32
   if (!st.position || !st.logdensity || !st.logdensity_grad || C < 0) { set_error("init: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
   if (target->kind == GB200_TARGET_LOGREG) return launch_init_logreg(*target, st, C, dtype, (cudaStream_t)stream);
   LayoutChoice lay;
-  if (!choose_layout(target->D, 0, C, &lay)) { set_error("init: D=%d too large", target->D); return GB200_ERR_UNSUPPORTED; }
+  if (!choose_layout(target->D, dtype == GB200_F64 ? 1 : 0, C, &lay)) { set_error("init: D=%d too large", target->D); return GB200_ERR_UNSUPPORTED; }
   return launch_init(*target, st, C, lay, dtype, (cudaStream_t)stream);
 }
 
@@ -217,7 +217,7 @@ int gb200_step(int32_t sampler, const gb200_kernel_params* p, const gb200_target
     return GB200_ERR_UNSUPPORTED;
   }
   LayoutChoice lay;
-  if (!choose_layout(target->D, p->lanes_per_chain, C, &lay)) {
+  if (!choose_layout(target->D, p->dtype == GB200_F64 ? 1 : p->lanes_per_chain, C, &lay)) {
     set_error("step: no layout for D=%d lanes_per_chain=%d", target->D, p->lanes_per_chain);
     return GB200_ERR_UNSUPPORTED;
   }

@@ -42,8 +42,19 @@ static int launch_init_t(const Target& tg, gb200_state st, long long C, int D, L
 }
 
 int GB_LPC_NAME(launch_init)(const gb200_target_desc& t, gb200_state st, long long C, LayoutChoice lay, int dtype, cudaStream_t s) {
+  if (dtype == GB200_F64) {  // float64 (jax_enable_x64): funnel target, one lane per chain
+#if GB_LPC == 1
+    if (t.kind == GB200_TARGET_FUNNEL) {
+      Funnel<double> tg;
+      tg.setup(t);
+      return launch_init_t<double>(tg, st, C, t.D, lay, s);
+    }
+#endif
+    set_error("init: float64 is built for the funnel target with one lane per chain (D <= 32)");
+    return GB200_ERR_UNSUPPORTED;
+  }
   if (dtype != GB200_F32) {
-    set_error("init: only float32 is built in this version");
+    set_error("init: unknown dtype %d", dtype);
     return GB200_ERR_UNSUPPORTED;
   }
   switch (t.kind) {

@@ -43,9 +43,37 @@ static int launch_lmcmonge_t(const TransArgs& a, const Target& tg, LayoutChoice 
   return GB200_ERR_UNSUPPORTED;
 }
 
+// float64 instantiations (jax_enable_x64 parity, north-star tolerance rel 1e-10): one lane per chain, three
+// register-array sizes.  The normal / uniform draws of a float64 launch are the float32 streams widened
+// (JAX's 64-bit draws are not restated); parity tests pass the oracle's draws as overrides.
+#define GB_F64_LAYOUTS(X) X(2) X(8) X(20) X(32)
+#if GB_LPC == 1
+static int launch_lmcmonge_f64(const TransArgs& a, const Funnel<double>& tg, cudaStream_t s) {
+  int grid, block;
+  launch_shape(a.C, 1, &grid, &block);
+#define GB_X(E)                                                                                                   \
+  if (a.D <= E) {                                                                                                 \
+    lmcmonge_kernel<double, Funnel<double>, E, 1, false, false><<<grid, block, (size_t)block * E * sizeof(double), s>>>(a, tg); \
+    GB_CHECK_LAUNCH();                                                                                            \
+    return GB200_OK;                                                                                              \
+  }
+  GB_F64_LAYOUTS(GB_X)
+#undef GB_X
+  set_error("lmcmonge: float64 is built for D <= 32");
+  return GB200_ERR_UNSUPPORTED;
+}
+#endif
+
 int GB_LPC_NAME(launch_lmcmonge)(const TransArgs& a, const gb200_target_desc& t, LayoutChoice lay, int dtype, cudaStream_t s) {
-  if (dtype != GB200_F32) {
-    set_error("lmcmonge: only float32 is built in this version");
+  if (dtype == GB200_F64) {
+#if GB_LPC == 1
+    if (t.kind == GB200_TARGET_FUNNEL) {
+      Funnel<double> tg;
+      tg.setup(t);
+      return launch_lmcmonge_f64(a, tg, s);
+    }
+#endif
+    set_error("lmcmonge: float64 is built for the funnel target with one lane per chain (D <= 32)");
     return GB200_ERR_UNSUPPORTED;
   }
   switch (t.kind) {

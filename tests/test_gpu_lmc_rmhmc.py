@@ -201,3 +201,47 @@ def test_lean_fused_kernels_equal_stepwise(cuda, sampler, D):
     for a_, b_ in zip(fst, st):
         assert bool((a_ == b_).all())
     assert float((samples[-1] != samples[0]).float().mean()) > 0.5  # chains actually moved
+
+
+@pytest.mark.parametrize("sampler", ["lmc", "rmhmc", "lmcmonge"])
+@pytest.mark.parametrize("D,C", [(2, 64), (8, 33), (20, 40), (27, 9)])
+def test_float64_single_step_rel_1e10(cuda, sampler, D, C):
+    """jax_enable_x64 parity (north-star tolerance rel 1e-10): the float64 instantiations against the
+    float64 oracle, one integrator step, same keys (a float64 launch widens the float32 draws)."""
+    import torch
+    import geomjax_b200 as g
+    q32, keys = _setup(D, C, seed=3 * D + 1)
+    q = q32.astype(np.float64)
+    t32, t64 = T.NealFunnel(D), T.NealFunnel(D, dtype=np.float64)
+    eps = 0.05 / np.sqrt(D)
+    km, ka = S._draw_keys(keys, P.LEGACY)
+    z = np.stack([P.normal(km[c], (D,)) for c in range(C)]).astype(np.float64)
+    u = np.array([P.uniform(ka[c]) for c in range(C)], np.float64)
+    target = g.neal_funnel(D)
+    qd = _t(q, cuda)
+    if sampler == "lmc":
+        onew, oi = S.lmc_step(keys, S.lmc_init(q, t64), t64, eps, 1, z=z, u=u)
+        alg = g.lmc(target, eps, target, 1)
+    elif sampler == "rmhmc":
+        onew, oi = S.rmhmc_step(keys, S.rmhmc_init(q, t64), t64, eps, 1, z=z, u=u)
+        alg = g.rmhmc(target, eps, target, 1)
+    else:
+        onew, oi = S.lmcmonge_step(keys, S.lmcmonge_init(q, t64), t64, eps, np.ones(D), 1, z=z, u=u,
+                                   half_step="omega_fixed")
+        alg = g.lmcmonge(target, eps, torch.ones(D, device=cuda, dtype=torch.float64), 1,
+                         integrator=g.integrators.half_step_omega_fixed)
+    st = alg.init(qd)
+    assert st.position.dtype == torch.float64 and st.logdensity.dtype == torch.float64
+    new, info = alg.step(_t(keys, cuda), st)
+    n = lambda t: t.cpu().numpy()
+    ps = info.proposal.state
+    draw = info.momentum if sampler == "rmhmc" else info.velocity
+    np.testing.assert_allclose(n(draw), oi.momentum, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(n(ps.position), oi.proposal["position"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(n(ps.logdensity), oi.proposal["logdensity"], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(n(info.energy), oi.energy, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(n(info.acceptance_rate), oi.acceptance_rate, rtol=1e-9, atol=1e-10)
+    np.testing.assert_array_equal(n(info.is_accepted), oi.is_accepted)
+    np.testing.assert_allclose(n(new.position), onew.position, rtol=1e-10, atol=1e-12)
+    if sampler != "rmhmc":
+        np.testing.assert_allclose(n(ps.volume_adjustment), oi.proposal["volume_adjustment"], rtol=1e-9, atol=1e-11)
