@@ -50,51 +50,62 @@ __global__ void k_rhat_partial(const R* __restrict__ x, long long T, long long C
 }
 
 // ---- ESS partial: chain-summed biased autocovariance for lag < num_lags.
-// One block = one dimension d and S chains whose centred series sit in shared memory; thread l
-// accumulates lag l over all S series and issues one atomic per (block, lag).
+// One block = one dimension d and up to 32 chains whose centred series sit in shared memory with an odd,
+// zero-padded stride TS.  A warp owns a block of 8 consecutive lags, its lanes own the 32 series: per 8
+// time steps a lane loads a[0..7] = p[t..t+7] and b[0..14] = p[t+l..t+l+14] from ITS series (bank =
+// (9 s + t) mod 32: conflict-free) and issues 64 FMAs -- 0.36 shared loads per FMA with every thread
+// busy (the first version ran one thread per lag: 2 loads per FMA and 64 active threads at 64 lags).
+// The zero padding makes every out-of-range product vanish, so there is no bounds logic in the loop.
 template <typename R>
-__global__ void k_ess_partial(const R* __restrict__ x, long long T, long long C, int D, int num_lags, int S,
-                              double* acov) {
-  extern __shared__ float xs[];  // S * T
+__global__ void __launch_bounds__(256) k_ess_partial(const R* __restrict__ x, long long T, long long C, int D,
+                                                     int num_lags, int S, int TS, double* acov) {
+  extern __shared__ float xs[];  // S * TS
   const int d = blockIdx.y;
   const long long c0 = (long long)blockIdx.x * S;
   const int ns = (int)min((long long)S, C - c0);
   const long long CD = C * D;
+  for (long long i = threadIdx.x; i < (long long)S * TS; i += blockDim.x) xs[i] = 0.f;
+  __syncthreads();
   for (long long i = threadIdx.x; i < (long long)ns * T; i += blockDim.x) {
     const int s = (int)(i % ns);
     const long long t = i / ns;
-    xs[(long long)s * T + t] = (float)x[t * CD + (c0 + s) * D + d];
+    xs[(long long)s * TS + t] = (float)x[t * CD + (c0 + s) * D + d];
   }
   __syncthreads();
   // centre each series on its own mean (diagnostics.py:122-124)
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarp = blockDim.x / 32;
   for (int s = warp; s < ns; s += nwarp) {
     double sum = 0.0;
-    for (long long t = lane; t < T; t += 32) sum += (double)xs[(long long)s * T + t];
+    for (long long t = lane; t < T; t += 32) sum += (double)xs[(long long)s * TS + t];
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float m = (float)(sum / (double)T);
-    for (long long t = lane; t < T; t += 32) xs[(long long)s * T + t] -= m;
+    for (long long t = lane; t < T; t += 32) xs[(long long)s * TS + t] -= m;
   }
   __syncthreads();
-  for (int l = threadIdx.x; l < num_lags; l += blockDim.x) {
-    double tot = 0.0;
-    if (l < T) {
-      for (int s = 0; s < ns; ++s) {
-        const float* p = xs + (long long)s * T;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        long long t = 0;
-        const long long n = T - l;
-        for (; t + 3 < n; t += 4) {
-          a0 = fmaf(p[t], p[t + l], a0);
-          a1 = fmaf(p[t + 1], p[t + 1 + l], a1);
-          a2 = fmaf(p[t + 2], p[t + 2 + l], a2);
-          a3 = fmaf(p[t + 3], p[t + 3 + l], a3);
-        }
-        for (; t < n; ++t) a0 = fmaf(p[t], p[t + l], a0);
-        tot += (double)((a0 + a1) + (a2 + a3));
-      }
+  const bool live = lane < ns;                       // S may be smaller than a warp
+  const float* p = xs + (long long)(live ? lane : 0) * TS;
+  for (int l0 = 8 * warp; l0 < num_lags; l0 += 8 * nwarp) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const long long n = T - l0;  // products with t >= T - l0 are all zero
+    for (long long t = 0; t < n; t += 8) {
+      float a[8], bb[15];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = p[t + i];
+#pragma unroll
+      for (int i = 0; i < 15; ++i) bb[i] = p[t + l0 + i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j] = fmaf(a[i], bb[i + j], acc[j]);
     }
-    atomicAdd(&acov[(long long)l * D + d], tot / (double)T);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double tot = live ? (double)acc[j] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (lane == 0 && l0 + j < num_lags) atomicAdd(&acov[(long long)(l0 + j) * D + d], tot / (double)T);
+    }
   }
 }
 
@@ -142,20 +153,21 @@ int gb200_ess_partial(const void* samples, int64_t T, int64_t C, int32_t D, int3
   if (num_lags > T) num_lags = (int32_t)T;
   cudaMemsetAsync(acov, 0, sizeof(double) * (size_t)num_lags * D, s);
   const size_t max_sh = 200 * 1024;
-  long long S = (long long)(max_sh / (sizeof(float) * (size_t)T));
+  const long long TS = ((T + 24) | 1);  // odd stride, >= 24 floats of zero padding behind every series
+  long long S = (long long)(max_sh / (sizeof(float) * (size_t)TS));
   if (S < 1) { set_error("ess_partial: T=%lld too long for the shared-memory series tile", (long long)T); return GB200_ERR_UNSUPPORTED; }
   if (S > 32) S = 32;
   if (S > C) S = C;
-  const size_t sh = sizeof(float) * (size_t)S * (size_t)T;
+  const size_t sh = sizeof(float) * (size_t)S * (size_t)TS;
   dim3 grid((unsigned)((C + S - 1) / S), (unsigned)D);
   const int block = 256;
   cudaError_t e;
   if (dtype == GB200_F32) {
     e = cudaFuncSetAttribute(k_ess_partial<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-    if (e == cudaSuccess) k_ess_partial<float><<<grid, block, sh, s>>>((const float*)samples, T, C, D, num_lags, (int)S, acov);
+    if (e == cudaSuccess) k_ess_partial<float><<<grid, block, sh, s>>>((const float*)samples, T, C, D, num_lags, (int)S, (int)TS, acov);
   } else {
     e = cudaFuncSetAttribute(k_ess_partial<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-    if (e == cudaSuccess) k_ess_partial<double><<<grid, block, sh, s>>>((const double*)samples, T, C, D, num_lags, (int)S, acov);
+    if (e == cudaSuccess) k_ess_partial<double><<<grid, block, sh, s>>>((const double*)samples, T, C, D, num_lags, (int)S, (int)TS, acov);
   }
   if (e != cudaSuccess) { set_error("ess_partial: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
   GB_CHECK_LAUNCH();
