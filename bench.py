@@ -93,7 +93,7 @@ def run_reference(args, cfg):
     # calibrate the per-step sample so that warmup + steps finish within a few minutes
     v, wall = oracle_throughput(cfg, cpw, 1, cores)
     per_transition = wall
-    tps = max(1, int(8.0 / max(per_transition, 1e-3)))  # ~8 s of wall per step
+    tps = max(1, int(4.0 / max(per_transition, 1e-3)))  # ~4 s of wall per step: K = 20 steps stay within ~2 minutes
     tps = min(tps, 64)
     for _ in range(args.warmup):
         oracle_throughput(cfg, cpw, 1, cores)
