@@ -57,42 +57,84 @@ __device__ __forceinline__ void ft_split(float a, float& hi, float& lo) {
   lo = __uint_as_float(__float_as_uint(a - hi) & 0xFFFFE000u);       // TF32-truncated remainder
 }
 
-// W[c, n] = s(1-s),  s = sigmoid(x_n . theta_c);  one thread per (chain, data row)
-__global__ void fisher_weights_kernel(const float* __restrict__ Xt, int ldx, int N, int D, const float* __restrict__ theta,
-                                      long long C, float* __restrict__ W, int ldw) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long c = idx / ldw;
-  const int n = (int)(idx - c * ldw);
-  if (c >= C) return;
-  float w = 0.f;
-  if (n < N) {
-    float eta = 0.f;
-    for (int i = 0; i < D; ++i) eta = fmaf(Xt[(size_t)i * ldx + n], theta[c * D + i], eta);
-    const float s = 1.f / (1.f + expf(-eta));
-    w = s * (1.f - s);
+// ---- operand B: W^T tiles, pre-split and pre-laid-out --------------------------------------------------
+// w[c, n] = s(1-s), s = sigmoid(x_n . theta_c), written ONCE per call as TF32 hi / lo parts directly in the
+// UMMA canonical K-major tile layout, one 32 KB block per (chain tile of 128, K tile of 32 data rows):
+// [hi tile 16 KB][lo tile 16 KB].  The GEMM kernel then fetches a B stage with ONE bulk-TMA copy instead
+// of 128 threads issuing 32 scattered loads + splits each.  One thread = (chain, 4 consecutive data rows)
+// = one 16-byte core-matrix row; 64 consecutive threads write one contiguous 1 KB row group.
+__global__ void __launch_bounds__(256)
+fisher_weights_kernel(const float* __restrict__ Xt, int ldx, int N, int D, const float* __restrict__ theta,
+                      long long C, unsigned char* __restrict__ Wt, int ktiles, long long ctiles) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long tile = gid >> 10;  // 1024 threads per (chain tile, K tile): 128 rows x 8 k-quads
+  if (tile >= ctiles * ktiles) return;
+  const int l = (int)(gid & 1023);
+  const int rg = l >> 6, row = rg * 8 + (l & 7), kq = (l >> 3) & 7;
+  const long long ct = tile / ktiles;
+  const int kt = (int)(tile - ct * ktiles);
+  const long long c = ct * FT_N + row;
+  const int n = kt * FT_KT + 4 * kq;
+  float w[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C && n < N) {
+    float eta[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* th = theta + c * D;
+    for (int i = 0; i < D; ++i) {
+      const float4 x = __ldg((const float4*)(Xt + (size_t)i * ldx + n));  // ldx % 4 == 0, columns >= N are zero
+      const float t = __ldg(th + i);
+      eta[0] = fmaf(x.x, t, eta[0]); eta[1] = fmaf(x.y, t, eta[1]);
+      eta[2] = fmaf(x.z, t, eta[2]); eta[3] = fmaf(x.w, t, eta[3]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float sg = 1.f / (1.f + expf(-eta[e]));
+      w[e] = (n + e < N) ? sg * (1.f - sg) : 0.f;
+    }
   }
-  W[c * ldw + n] = w;  // rows N..ldw-1 are zero padding (K is processed in tiles of FT_KT)
+  float4 hi, lo;
+  ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
+  unsigned char* base = Wt + (size_t)tile * (2 * FT_TILE_BYTES) + (size_t)rg * FT_SBO + kq * FT_LBO + (l & 7) * 16;
+  *(float4*)base = hi;
+  *(float4*)(base + FT_TILE_BYTES) = lo;
 }
 
+__device__ __forceinline__ void ft_mbar_wait(uint32_t mbar_a, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar_a), "r"(parity)
+        : "memory");
+  }
+}
+
+// ---- the GEMM: two operand stages, two TMEM accumulators ------------------------------------------------
+// Per K tile (32 data rows): wait until the MMAs that read this stage two tiles ago are done; one thread
+// starts the bulk copy of the B stage; all threads stage the X tile and build the Khatri-Rao A stage
+// (thread = pair row); one thread issues the 12 MMAs (3xTF32 x 4 K-steps) and commits -- nobody waits
+// for them: the next tile's build overlaps this tile's MMAs.  Every FT_KC tiles the finished chunk is
+// drained from its TMEM accumulator into FP32 registers (two-level accumulation, see below) while the
+// tensor core already works on the next chunk in the other accumulator.
 __global__ void __launch_bounds__(FT_THREADS, 1)
-fisher_metric_tc_kernel(const float* __restrict__ Xt, int ldx, int N, int D, const float* __restrict__ W, int ldw,
+fisher_metric_tc_kernel(const float* __restrict__ Xt, int ldx, int N, int D, const unsigned char* __restrict__ Wt,
                         long long C, float alpha, float* __restrict__ G) {
   extern __shared__ __align__(1024) unsigned char ft_smem[];
-  unsigned char* A_hi = ft_smem;
-  unsigned char* A_lo = A_hi + FT_TILE_BYTES;
-  unsigned char* B_hi = A_lo + FT_TILE_BYTES;
-  unsigned char* B_lo = B_hi + FT_TILE_BYTES;
-  float* xs = (float*)(B_lo + FT_TILE_BYTES);  // [D][FT_KT] staged X tile
+  // stage s: [A_hi | A_lo | B_hi | B_lo] (B_hi | B_lo contiguous: one bulk copy)
+  unsigned char* stage0 = ft_smem;
+  float* xs = (float*)(ft_smem + 2 * 4 * FT_TILE_BYTES);  // [D][FT_KT] staged X tile
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ __align__(8) unsigned long long mbar[6];  // 0,1: stage free; 2,3: B landed; 4,5: accumulator complete
   const int tid = threadIdx.x, warp = tid >> 5;
   const int P = D * (D + 1) / 2;
-  const int m0 = blockIdx.x * FT_M;          // first pair of this CTA
-  const long long c0 = (long long)blockIdx.y * FT_N;  // first chain of this CTA
-  const uint32_t mbar_a = (uint32_t)__cvta_generic_to_shared(&mbar);
+  const int m0 = blockIdx.x * FT_M;                    // first pair of this CTA
+  const long long ct = blockIdx.y;                     // chain tile
+  const long long c0 = ct * FT_N;
+  uint32_t mb[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) mb[i] = (uint32_t)__cvta_generic_to_shared(&mbar[i]);
 
-  // pair (i, j), i <= j, handled by this thread (row m0 + tid of the A tile)
-  int pi = 0, pj = 0;
+  int pi = 0, pj = 0;  // pair (i, j), i <= j, of row m0 + tid
   {
     int m = m0 + tid;
     if (m < P) {
@@ -108,11 +150,12 @@ fisher_metric_tc_kernel(const float* __restrict__ Xt, int ldx, int N, int D, con
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      (uint32_t)__cvta_generic_to_shared(&tmem_base_s)),
-                 "n"(FT_N));
+                 "n"(2 * FT_N));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
+#pragma unroll
+    for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb[i]));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -120,8 +163,6 @@ fisher_metric_tc_kernel(const float* __restrict__ Xt, int ldx, int N, int D, con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
 
-  const uint32_t a_hi_s = (uint32_t)__cvta_generic_to_shared(A_hi), a_lo_s = (uint32_t)__cvta_generic_to_shared(A_lo);
-  const uint32_t b_hi_s = (uint32_t)__cvta_generic_to_shared(B_hi), b_lo_s = (uint32_t)__cvta_generic_to_shared(B_lo);
   // Two-level accumulation.  The tensor core adds partial products into TMEM with truncation, a
   // bias that grows linearly with the number of accumulated K steps (measured: 2.3e-5 relative at
   // N = 1000, 4.5e-5 at N = 2000).  Every FT_KC stages (128 data rows) the chunk is drained from TMEM
@@ -130,82 +171,98 @@ fisher_metric_tc_kernel(const float* __restrict__ Xt, int ldx, int N, int D, con
 #pragma unroll
   for (int e = 0; e < FT_N; ++e) acc[e] = 0.f;
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  uint32_t phase = 0;
   const int ktiles = (N + FT_KT - 1) / FT_KT;
+  const int nchunks = (ktiles + FT_KC - 1) / FT_KC;
+
+  auto drain = [&](int chunk) {  // accumulator (chunk & 1) -> registers; all threads
+    ft_mbar_wait(mb[4 + (chunk & 1)], (uint32_t)((chunk >> 1) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t col0 = (uint32_t)((chunk & 1) * FT_N);
+#pragma unroll
+    for (int col = 0; col < FT_N; col += 8) {
+      uint32_t r[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                   : "r"(tmem_d + lane_base + col0 + (uint32_t)col));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[col + e] += __uint_as_float(r[e]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  };
+
   for (int kt = 0; kt < ktiles; ++kt) {
+    const int s = kt & 1, use = kt >> 1;
+    unsigned char* A_hi = stage0 + (size_t)s * 4 * FT_TILE_BYTES;
+    unsigned char* A_lo = A_hi + FT_TILE_BYTES;
+    unsigned char* B_hi = A_lo + FT_TILE_BYTES;
     const int n0 = kt * FT_KT;
-    // stage the X tile [D][KT] (zero beyond N)
+    if (kt >= 2) ft_mbar_wait(mb[s], (uint32_t)((use - 1) & 1));  // MMAs of tile kt - 2 have read this stage
+    if (tid == 0) {
+      const uint32_t bytes = 2 * FT_TILE_BYTES;
+      const unsigned char* src = Wt + ((size_t)ct * ktiles + kt) * bytes;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb[2 + s]), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(B_hi)),
+                   "l"(src), "r"(bytes), "r"(mb[2 + s])
+                   : "memory");
+    }
+    // stage the X tile [D][KT] (zero beyond N); the previous tile's A build finished at its last barrier
     for (int e = tid; e < D * FT_KT; e += FT_THREADS) {
       const int i = e / FT_KT, kk = e - i * FT_KT;
       xs[e] = (n0 + kk < N) ? Xt[(size_t)i * ldx + n0 + kk] : 0.f;
     }
     __syncthreads();
-    // A tile: row = pair, z = x_i * x_j over the KT data rows
-#pragma unroll 4
-    for (int kk = 0; kk < FT_KT; ++kk) {
-      const float a = (pi >= 0) ? xs[pi * FT_KT + kk] * xs[pj * FT_KT + kk] : 0.f;
-      float hi, lo;
-      ft_split(a, hi, lo);
-      const int off = ft_off(tid, kk);
-      *(float*)(A_hi + off) = hi;
-      *(float*)(A_lo + off) = lo;
-    }
-    // B tile: row = chain, w over the KT data rows (W rows are padded with zeros up to ldw)
+    // A stage: row = pair, z = x_i * x_j over the KT data rows
     {
-      const long long c = c0 + tid;
-      const float* wrow = W + (size_t)(c < C ? c : 0) * ldw + n0;
-#pragma unroll 4
-      for (int kk = 0; kk < FT_KT; ++kk) {
-        const float b = (c < C && n0 + kk < ldw) ? wrow[kk] : 0.f;
-        float hi, lo;
-        ft_split(b, hi, lo);
-        const int off = ft_off(tid, kk);
-        *(float*)(B_hi + off) = hi;
-        *(float*)(B_lo + off) = lo;
+      const float* xi = xs + (pi >= 0 ? pi : 0) * FT_KT;
+      const float* xj = xs + (pi >= 0 ? pj : 0) * FT_KT;
+#pragma unroll
+      for (int k4 = 0; k4 < FT_KT / 4; ++k4) {
+        const float4 a4 = *(const float4*)(xi + 4 * k4);
+        const float4 b4 = *(const float4*)(xj + 4 * k4);
+        float4 hi, lo;
+        const bool ok = pi >= 0;
+        ft_split(ok ? a4.x * b4.x : 0.f, hi.x, lo.x);
+        ft_split(ok ? a4.y * b4.y : 0.f, hi.y, lo.y);
+        ft_split(ok ? a4.z * b4.z : 0.f, hi.z, lo.z);
+        ft_split(ok ? a4.w * b4.w : 0.f, hi.w, lo.w);
+        const int off = (tid >> 3) * FT_SBO + k4 * FT_LBO + (tid & 7) * 16;
+        *(float4*)(A_hi + off) = hi;
+        *(float4*)(A_lo + off) = lo;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
+      ft_mbar_wait(mb[2 + s], (uint32_t)(use & 1));  // B stage landed
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi_s = (uint32_t)__cvta_generic_to_shared(A_hi), a_lo_s = a_hi_s + FT_TILE_BYTES;
+      const uint32_t b_hi_s = a_lo_s + FT_TILE_BYTES, b_lo_s = b_hi_s + FT_TILE_BYTES;
+      const int chunk = kt / FT_KC;
+      const uint32_t td = tmem_d + (uint32_t)((chunk & 1) * FT_N);
 #pragma unroll
       for (int k8 = 0; k8 < FT_KT / 8; ++k8) {
         const uint32_t adv = (uint32_t)k8 * 2u * FT_LBO;  // one MMA consumes 8 tf32 = 2 core matrices along K
         const uint32_t acc0 = ((kt % FT_KC) > 0 || k8 > 0) ? 1u : 0u;
-        ft_mma(tmem_d, ft_smem_desc(a_hi_s + adv), ft_smem_desc(b_hi_s + adv), acc0);
-        ft_mma(tmem_d, ft_smem_desc(a_hi_s + adv), ft_smem_desc(b_lo_s + adv), 1u);
-        ft_mma(tmem_d, ft_smem_desc(a_lo_s + adv), ft_smem_desc(b_hi_s + adv), 1u);
+        ft_mma(td, ft_smem_desc(a_hi_s + adv), ft_smem_desc(b_hi_s + adv), acc0);
+        ft_mma(td, ft_smem_desc(a_hi_s + adv), ft_smem_desc(b_lo_s + adv), 1u);
+        ft_mma(td, ft_smem_desc(a_lo_s + adv), ft_smem_desc(b_hi_s + adv), 1u);
       }
-      // arrives on the mbarrier when every MMA issued so far has finished reading shared memory
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_a) : "memory");
+      // arrives when every MMA issued so far has finished reading shared memory / writing TMEM
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb[s]) : "memory");
+      if ((kt % FT_KC) == FT_KC - 1 || kt == ktiles - 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb[4 + (chunk & 1)]) : "memory");
     }
-    // single-buffered: wait until the tensor core is done with this stage's operands
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(done)
-          : "r"(mbar_a), "r"(phase)
-          : "memory");
-    }
-    phase ^= 1u;
-    if ((kt % FT_KC) == FT_KC - 1 || kt == ktiles - 1) {
-      // drain the chunk: TMEM -> registers (warp w owns lanes 32w..32w+31; thread = pair row)
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int col = 0; col < FT_N; col += 8) {
-        uint32_t r[8];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                     : "r"(tmem_d + lane_base + (uint32_t)col));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[col + e] += __uint_as_float(r[e]);
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();  // every warp has drained before the next chunk's first MMA overwrites TMEM
+    // first tile of a new chunk is in flight: drain the previous chunk's accumulator under it
+    if ((kt % FT_KC) == 0 && kt > 0) {
+      drain(kt / FT_KC - 1);
+      // (the __syncthreads of the following tiles order this drain before the accumulator's next overwrite,
+      //  which is issued FT_KC tiles later)
     }
   }
+  drain(nchunks - 1);
 
   // epilogue: registers -> G[c, i, j] (+ alpha on the diagonal)
   if (pi >= 0) {
@@ -223,7 +280,7 @@ fisher_metric_tc_kernel(const float* __restrict__ Xt, int ldx, int N, int D, con
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(FT_N));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(2 * FT_N));
   }
 }
 
@@ -238,28 +295,31 @@ extern "C" int gb200_logreg_fisher_metric(const gb200_target_desc* t, const void
   if (C == 0) return GB200_OK;
   if (!position || !metric || !workspace || C < 0 || !t->vec0) { set_error("fisher_metric: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
   const int N = (int)t->N, D = t->D, ldx = (int)t->params[1];
-  const int ldw = (N + FT_KT - 1) / FT_KT * FT_KT;
-  const int64_t need = (int64_t)C * ldw * 4;
+  const int ktiles = (N + FT_KT - 1) / FT_KT;
+  const long long ctiles = (C + FT_N - 1) / FT_N;
+  const int64_t need = (int64_t)ctiles * ktiles * 2 * FT_TILE_BYTES;
   if (workspace_bytes < need) { set_error("fisher_metric: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)need); return GB200_ERR_INVALID_ARGUMENT; }
+  if (ldx % 4 != 0 || ((uintptr_t)workspace & 15) != 0) { set_error("fisher_metric: ldx must be a multiple of 4 and the workspace 16-byte aligned"); return GB200_ERR_INVALID_ARGUMENT; }
   cudaStream_t s = (cudaStream_t)stream;
-  float* W = (float*)workspace;
+  unsigned char* Wt = (unsigned char*)workspace;
   {
-    const long long total = (long long)C * ldw;
-    fisher_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float*)t->vec0, ldx, N, D, (const float*)position, C, W, ldw);
+    const long long total = ctiles * ktiles * 1024;
+    fisher_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float*)t->vec0, ldx, N, D, (const float*)position, C, Wt, ktiles, ctiles);
     GB_CHECK_LAUNCH();
   }
   const int P = D * (D + 1) / 2;
-  const size_t smem = 4 * FT_TILE_BYTES + (size_t)D * FT_KT * 4 + 1024;
+  const size_t smem = 8 * FT_TILE_BYTES + (size_t)D * FT_KT * 4 + 1024;
   cudaError_t e = cudaFuncSetAttribute(fisher_metric_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("fisher_metric: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
-  dim3 grid((unsigned)((P + FT_M - 1) / FT_M), (unsigned)((C + FT_N - 1) / FT_N));
-  fisher_metric_tc_kernel<<<grid, FT_THREADS, smem, s>>>((const float*)t->vec0, ldx, N, D, W, ldw, C, (float)t->params[0], (float*)metric);
+  dim3 grid((unsigned)((P + FT_M - 1) / FT_M), (unsigned)ctiles);
+  fisher_metric_tc_kernel<<<grid, FT_THREADS, smem, s>>>((const float*)t->vec0, ldx, N, D, Wt, C, (float)t->params[0], (float*)metric);
   GB_CHECK_LAUNCH();
   return GB200_OK;
 }
 
 extern "C" int64_t gb200_logreg_fisher_metric_workspace(const gb200_target_desc* t, int64_t C) {
   if (!t) return 0;
-  const int ldw = ((int)t->N + FT_KT - 1) / FT_KT * FT_KT;
-  return (int64_t)C * ldw * 4;
+  const int64_t ktiles = ((int64_t)t->N + FT_KT - 1) / FT_KT;
+  const int64_t ctiles = (C + FT_N - 1) / FT_N;
+  return ctiles * ktiles * 2 * FT_TILE_BYTES;  // pre-split W^T tiles (hi + lo), see fisher_weights_kernel
 }
