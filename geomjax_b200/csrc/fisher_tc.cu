@@ -98,6 +98,18 @@ fisher_weights_kernel(const float* __restrict__ Xt, int ldx, int N, int D, const
   *(float4*)(base + FT_TILE_BYTES) = lo;
 }
 
+// X re-tiled per K tile: Xtile[kt][i][kk] = X[kt*32 + kk, i] (zero beyond N), so that the GEMM kernel fetches
+// a whole [D][32] tile with one bulk copy (its per-tile staging loop was 30% of all stall samples).
+__global__ void fisher_xtile_kernel(const float* __restrict__ Xt, int ldx, int N, int D, float* __restrict__ Xtile, int ktiles) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)ktiles * D * FT_KT) return;
+  const int kk = (int)(e % FT_KT);
+  const long long r = e / FT_KT;
+  const int i = (int)(r % D), kt = (int)(r / D);
+  const int n = kt * FT_KT + kk;
+  Xtile[e] = (n < N) ? Xt[(size_t)i * ldx + n] : 0.f;
+}
+
 __device__ __forceinline__ void ft_mbar_wait(uint32_t mbar_a, uint32_t parity) {
   uint32_t done = 0;
   while (!done) {
@@ -117,22 +129,23 @@ __device__ __forceinline__ void ft_mbar_wait(uint32_t mbar_a, uint32_t parity) {
 // drained from its TMEM accumulator into FP32 registers (two-level accumulation, see below) while the
 // tensor core already works on the next chunk in the other accumulator.
 __global__ void __launch_bounds__(FT_THREADS, 1)
-fisher_metric_tc_kernel(const float* __restrict__ Xt, int ldx, int N, int D, const unsigned char* __restrict__ Wt,
+fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const unsigned char* __restrict__ Wt,
                         long long C, float alpha, float* __restrict__ G) {
   extern __shared__ __align__(1024) unsigned char ft_smem[];
   // stage s: [A_hi | A_lo | B_hi | B_lo] (B_hi | B_lo contiguous: one bulk copy)
   unsigned char* stage0 = ft_smem;
-  float* xs = (float*)(ft_smem + 2 * 4 * FT_TILE_BYTES);  // [D][FT_KT] staged X tile
+  float* xs0 = (float*)(ft_smem + 2 * 4 * FT_TILE_BYTES);  // two [D][FT_KT] X tiles (bulk-copied one tile ahead)
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(8) unsigned long long mbar[6];  // 0,1: stage free; 2,3: B landed; 4,5: accumulator complete
+  __shared__ __align__(8) unsigned long long mbar[8];  // 0,1: stage free; 2,3: B landed; 4,5: accumulator complete; 6,7: X landed
   const int tid = threadIdx.x, warp = tid >> 5;
   const int P = D * (D + 1) / 2;
   const int m0 = blockIdx.x * FT_M;                    // first pair of this CTA
   const long long ct = blockIdx.y;                     // chain tile
   const long long c0 = ct * FT_N;
-  uint32_t mb[6];
+  uint32_t mb[8];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) mb[i] = (uint32_t)__cvta_generic_to_shared(&mbar[i]);
+  for (int i = 0; i < 8; ++i) mb[i] = (uint32_t)__cvta_generic_to_shared(&mbar[i]);
+  const uint32_t xbytes = (uint32_t)D * FT_KT * 4;
 
   int pi = 0, pj = 0;  // pair (i, j), i <= j, of row m0 + tid
   {
@@ -155,7 +168,7 @@ fisher_metric_tc_kernel(const float* __restrict__ Xt, int ldx, int N, int D, con
   }
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb[i]));
+    for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb[i]));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -179,24 +192,40 @@ fisher_metric_tc_kernel(const float* __restrict__ Xt, int ldx, int N, int D, con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t col0 = (uint32_t)((chunk & 1) * FT_N);
 #pragma unroll
-    for (int col = 0; col < FT_N; col += 8) {
-      uint32_t r[8];
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                   : "r"(tmem_d + lane_base + col0 + (uint32_t)col));
+    for (int col = 0; col < FT_N; col += 32) {  // 32 columns per tcgen05.ld: 4 load/wait round trips per drain, not 16
+      uint32_t r[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(tmem_d + lane_base + col0 + (uint32_t)col));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[col + e] += __uint_as_float(r[e]);
+      for (int e = 0; e < 32; ++e) acc[col + e] += __uint_as_float(r[e]);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   };
 
+  auto fetch_x = [&](int kt) {  // thread 0: bulk copy of X tile kt into xs[kt & 1]
+    const uint32_t bar = mb[6 + (kt & 1)];
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(xbytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(xs0 + (size_t)(kt & 1) * D * FT_KT)),
+                 "l"(Xtile + (size_t)kt * D * FT_KT), "r"(xbytes), "r"(bar)
+                 : "memory");
+  };
+  if (tid == 0) fetch_x(0);
+
   for (int kt = 0; kt < ktiles; ++kt) {
     const int s = kt & 1, use = kt >> 1;
+    const float* xs = xs0 + (size_t)s * D * FT_KT;
     unsigned char* A_hi = stage0 + (size_t)s * 4 * FT_TILE_BYTES;
     unsigned char* A_lo = A_hi + FT_TILE_BYTES;
     unsigned char* B_hi = A_lo + FT_TILE_BYTES;
-    const int n0 = kt * FT_KT;
     if (kt >= 2) ft_mbar_wait(mb[s], (uint32_t)((use - 1) & 1));  // MMAs of tile kt - 2 have read this stage
     if (tid == 0) {
       const uint32_t bytes = 2 * FT_TILE_BYTES;
@@ -206,13 +235,11 @@ fisher_metric_tc_kernel(const float* __restrict__ Xt, int ldx, int N, int D, con
                        (uint32_t)__cvta_generic_to_shared(B_hi)),
                    "l"(src), "r"(bytes), "r"(mb[2 + s])
                    : "memory");
+      // next X tile into the other buffer: its last reader (the A build of tile kt - 1) finished before the
+      // barrier that closed iteration kt - 1
+      if (kt + 1 < ktiles) fetch_x(kt + 1);
     }
-    // stage the X tile [D][KT] (zero beyond N); the previous tile's A build finished at its last barrier
-    for (int e = tid; e < D * FT_KT; e += FT_THREADS) {
-      const int i = e / FT_KT, kk = e - i * FT_KT;
-      xs[e] = (n0 + kk < N) ? Xt[(size_t)i * ldx + n0 + kk] : 0.f;
-    }
-    __syncthreads();
+    ft_mbar_wait(mb[6 + s], (uint32_t)(use & 1));  // X tile kt landed
     // A stage: row = pair, z = x_i * x_j over the KT data rows
     {
       const float* xi = xs + (pi >= 0 ? pi : 0) * FT_KT;
@@ -297,7 +324,8 @@ extern "C" int gb200_logreg_fisher_metric(const gb200_target_desc* t, const void
   const int N = (int)t->N, D = t->D, ldx = (int)t->params[1];
   const int ktiles = (N + FT_KT - 1) / FT_KT;
   const long long ctiles = (C + FT_N - 1) / FT_N;
-  const int64_t need = (int64_t)ctiles * ktiles * 2 * FT_TILE_BYTES;
+  const int64_t wt_bytes = (int64_t)ctiles * ktiles * 2 * FT_TILE_BYTES;
+  const int64_t need = wt_bytes + (int64_t)ktiles * D * FT_KT * 4;
   if (workspace_bytes < need) { set_error("fisher_metric: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)need); return GB200_ERR_INVALID_ARGUMENT; }
   if (ldx % 4 != 0 || ((uintptr_t)workspace & 15) != 0) { set_error("fisher_metric: ldx must be a multiple of 4 and the workspace 16-byte aligned"); return GB200_ERR_INVALID_ARGUMENT; }
   cudaStream_t s = (cudaStream_t)stream;
@@ -307,12 +335,18 @@ extern "C" int gb200_logreg_fisher_metric(const gb200_target_desc* t, const void
     fisher_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float*)t->vec0, ldx, N, D, (const float*)position, C, Wt, ktiles, ctiles);
     GB_CHECK_LAUNCH();
   }
+  float* Xtile = (float*)(Wt + wt_bytes);
+  {
+    const long long total = (long long)ktiles * D * FT_KT;
+    fisher_xtile_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float*)t->vec0, ldx, N, D, Xtile, ktiles);
+    GB_CHECK_LAUNCH();
+  }
   const int P = D * (D + 1) / 2;
-  const size_t smem = 8 * FT_TILE_BYTES + (size_t)D * FT_KT * 4 + 1024;
+  const size_t smem = 8 * FT_TILE_BYTES + 2 * (size_t)D * FT_KT * 4 + 1024;
   cudaError_t e = cudaFuncSetAttribute(fisher_metric_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("fisher_metric: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
   dim3 grid((unsigned)((P + FT_M - 1) / FT_M), (unsigned)ctiles);
-  fisher_metric_tc_kernel<<<grid, FT_THREADS, smem, s>>>((const float*)t->vec0, ldx, N, D, Wt, C, (float)t->params[0], (float*)metric);
+  fisher_metric_tc_kernel<<<grid, FT_THREADS, smem, s>>>(Xtile, N, D, Wt, C, (float)t->params[0], (float*)metric);
   GB_CHECK_LAUNCH();
   return GB200_OK;
 }
@@ -321,5 +355,6 @@ extern "C" int64_t gb200_logreg_fisher_metric_workspace(const gb200_target_desc*
   if (!t) return 0;
   const int64_t ktiles = ((int64_t)t->N + FT_KT - 1) / FT_KT;
   const int64_t ctiles = (C + FT_N - 1) / FT_N;
-  return ctiles * ktiles * 2 * FT_TILE_BYTES;  // pre-split W^T tiles (hi + lo), see fisher_weights_kernel
+  // pre-split W^T tiles (hi + lo), see fisher_weights_kernel, + the re-tiled X (fisher_xtile_kernel)
+  return ctiles * ktiles * 2 * FT_TILE_BYTES + ktiles * (int64_t)t->D * FT_KT * 4;
 }
