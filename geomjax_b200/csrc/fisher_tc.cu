@@ -22,7 +22,8 @@ constexpr int FT_M = 128;      // pairs per CTA (MMA M)
 constexpr int FT_N = 128;      // chains per CTA (MMA N)
 constexpr int FT_KT = 32;      // data rows per stage
 constexpr int FT_KC = 4;       // stages per TMEM accumulation chunk (see the epilogue note)
-constexpr int FT_THREADS = 128;
+constexpr int FT_THREADS = 160;  // warps 0-3: operand producers + accumulator drainers; warp 4: TMA / MMA issuer
+constexpr int FT_XS = FT_KT + 4;  // padded row stride (floats) of the staged X tile: conflict-free float4 row reads
 constexpr int FT_LBO = 128;                  // bytes
 constexpr int FT_SBO = (FT_KT / 4) * 128;    // bytes
 constexpr int FT_TILE_BYTES = FT_M * FT_KT * 4;
@@ -102,12 +103,12 @@ fisher_weights_kernel(const float* __restrict__ Xt, int ldx, int N, int D, const
 // a whole [D][32] tile with one bulk copy (its per-tile staging loop was 30% of all stall samples).
 __global__ void fisher_xtile_kernel(const float* __restrict__ Xt, int ldx, int N, int D, float* __restrict__ Xtile, int ktiles) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)ktiles * D * FT_KT) return;
-  const int kk = (int)(e % FT_KT);
-  const long long r = e / FT_KT;
+  if (e >= (long long)ktiles * D * FT_XS) return;
+  const int kk = (int)(e % FT_XS);
+  const long long r = e / FT_XS;
   const int i = (int)(r % D), kt = (int)(r / D);
   const int n = kt * FT_KT + kk;
-  Xtile[e] = (n < N) ? Xt[(size_t)i * ldx + n] : 0.f;
+  Xtile[e] = (kk < FT_KT && n < N) ? Xt[(size_t)i * ldx + n] : 0.f;
 }
 
 __device__ __forceinline__ void ft_mbar_wait(uint32_t mbar_a, uint32_t parity) {
@@ -121,44 +122,38 @@ __device__ __forceinline__ void ft_mbar_wait(uint32_t mbar_a, uint32_t parity) {
   }
 }
 
-// ---- the GEMM: two operand stages, two TMEM accumulators ------------------------------------------------
-// Per K tile (32 data rows): wait until the MMAs that read this stage two tiles ago are done; one thread
-// starts the bulk copy of the B stage; all threads stage the X tile and build the Khatri-Rao A stage
-// (thread = pair row); one thread issues the 12 MMAs (3xTF32 x 4 K-steps) and commits -- nobody waits
-// for them: the next tile's build overlaps this tile's MMAs.  Every FT_KC tiles the finished chunk is
-// drained from its TMEM accumulator into FP32 registers (two-level accumulation, see below) while the
-// tensor core already works on the next chunk in the other accumulator.
+// ---- the GEMM: warp-specialised, two A stages, three B slots, two TMEM accumulators -----------------------
+// Producers (warps 0-3, thread = pair row = TMEM lane), per K tile kt (32 data rows):
+//   wait until the MMAs of tile kt-2 are done (A stage kt&1 and B slot (kt+1)%3 are free); thread 0 starts the
+//   bulk copy of B(kt+1); wait for the X tile (bulk-copied two tiles ahead by the issuer); build the Khatri-Rao
+//   A stage (z = x_i x_j, split into TF32 hi / lo) and ARRIVE on the stage's mbarrier -- no block-wide barrier.
+//   On the first tile of a chunk they then drain the previous chunk's TMEM accumulator into FP32 registers
+//   (two-level accumulation, see below) while the tensor core already works on the new chunk.
+// Issuer (warp 4, one lane): waits for "A built" + "B landed", issues the 12 MMAs (3xTF32 x 4 K-steps) from
+//   pre-built descriptors, commits to the stage's "free" mbarrier (and the accumulator's "complete" mbarrier at
+//   a chunk end), and refills the X buffer the producers just finished with.
 __global__ void __launch_bounds__(FT_THREADS, 1)
 fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const unsigned char* __restrict__ Wt,
                         long long C, float alpha, float* __restrict__ G) {
   extern __shared__ __align__(1024) unsigned char ft_smem[];
-  // stage s: [A_hi | A_lo | B_hi | B_lo] (B_hi | B_lo contiguous: one bulk copy)
-  unsigned char* stage0 = ft_smem;
-  float* xs0 = (float*)(ft_smem + 2 * 4 * FT_TILE_BYTES);  // two [D][FT_KT] X tiles (bulk-copied one tile ahead)
+  unsigned char* Astage = ft_smem;                                  // 2 x [A_hi | A_lo]
+  unsigned char* Bslot = ft_smem + 2 * 2 * FT_TILE_BYTES;           // 3 x [B_hi | B_lo] (one bulk copy each)
+  float* xs0 = (float*)(ft_smem + (2 * 2 + 3 * 2) * FT_TILE_BYTES);  // 2 x [D][FT_XS] X tiles
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(8) unsigned long long mbar[8];  // 0,1: stage free; 2,3: B landed; 4,5: accumulator complete; 6,7: X landed
+  // 0,1: A stage free (MMAs done); 2,3: A stage built; 4,5,6: B slot landed; 7,8: X tile landed; 9,10: accumulator complete
+  __shared__ __align__(8) unsigned long long mbar[11];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int P = D * (D + 1) / 2;
-  const int m0 = blockIdx.x * FT_M;                    // first pair of this CTA
-  const long long ct = blockIdx.y;                     // chain tile
+  const int m0 = blockIdx.x * FT_M;
+  const long long ct = blockIdx.y;
   const long long c0 = ct * FT_N;
-  uint32_t mb[8];
+  uint32_t mb[11];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) mb[i] = (uint32_t)__cvta_generic_to_shared(&mbar[i]);
-  const uint32_t xbytes = (uint32_t)D * FT_KT * 4;
-
-  int pi = 0, pj = 0;  // pair (i, j), i <= j, of row m0 + tid
-  {
-    int m = m0 + tid;
-    if (m < P) {
-      int i = 0, rem = m;
-      while (rem >= D - i) { rem -= D - i; ++i; }
-      pi = i;
-      pj = i + rem;
-    } else {
-      pi = -1;
-    }
-  }
+  for (int i = 0; i < 11; ++i) mb[i] = (uint32_t)__cvta_generic_to_shared(&mbar[i]);
+  const uint32_t xbytes = (uint32_t)D * FT_XS * 4;
+  const uint32_t bbytes = 2 * FT_TILE_BYTES;
+  const int ktiles = (N + FT_KT - 1) / FT_KT;
+  const int nchunks = (ktiles + FT_KC - 1) / FT_KC;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -168,7 +163,10 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
   }
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb[i]));
+    for (int i = 0; i < 11; ++i) {
+      const uint32_t cnt = (i == 2 || i == 3) ? 128u : 1u;  // "built": every producer thread arrives
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb[i]), "r"(cnt));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -176,131 +174,140 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
 
-  // Two-level accumulation.  The tensor core adds partial products into TMEM with truncation, a
-  // bias that grows linearly with the number of accumulated K steps (measured: 2.3e-5 relative at
-  // N = 1000, 4.5e-5 at N = 2000).  Every FT_KC stages (128 data rows) the chunk is drained from TMEM
-  // and added to FP32 register accumulators with round-to-nearest; the next chunk restarts at zero.
-  float acc[FT_N];
-#pragma unroll
-  for (int e = 0; e < FT_N; ++e) acc[e] = 0.f;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  const int ktiles = (N + FT_KT - 1) / FT_KT;
-  const int nchunks = (ktiles + FT_KC - 1) / FT_KC;
-
-  auto drain = [&](int chunk) {  // accumulator (chunk & 1) -> registers; all threads
-    ft_mbar_wait(mb[4 + (chunk & 1)], (uint32_t)((chunk >> 1) & 1));
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t col0 = (uint32_t)((chunk & 1) * FT_N);
-#pragma unroll
-    for (int col = 0; col < FT_N; col += 32) {  // 32 columns per tcgen05.ld: 4 load/wait round trips per drain, not 16
-      uint32_t r[32];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(tmem_d + lane_base + col0 + (uint32_t)col));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int e = 0; e < 32; ++e) acc[col + e] += __uint_as_float(r[e]);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  };
-
-  auto fetch_x = [&](int kt) {  // thread 0: bulk copy of X tile kt into xs[kt & 1]
-    const uint32_t bar = mb[6 + (kt & 1)];
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(xbytes) : "memory");
+  auto bulk = [&](void* dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(xs0 + (size_t)(kt & 1) * D * FT_KT)),
-                 "l"(Xtile + (size_t)kt * D * FT_KT), "r"(xbytes), "r"(bar)
+                     (uint32_t)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
   };
-  if (tid == 0) fetch_x(0);
 
-  for (int kt = 0; kt < ktiles; ++kt) {
-    const int s = kt & 1, use = kt >> 1;
-    const float* xs = xs0 + (size_t)s * D * FT_KT;
-    unsigned char* A_hi = stage0 + (size_t)s * 4 * FT_TILE_BYTES;
-    unsigned char* A_lo = A_hi + FT_TILE_BYTES;
-    unsigned char* B_hi = A_lo + FT_TILE_BYTES;
-    if (kt >= 2) ft_mbar_wait(mb[s], (uint32_t)((use - 1) & 1));  // MMAs of tile kt - 2 have read this stage
-    if (tid == 0) {
-      const uint32_t bytes = 2 * FT_TILE_BYTES;
-      const unsigned char* src = Wt + ((size_t)ct * ktiles + kt) * bytes;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb[2 + s]), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       (uint32_t)__cvta_generic_to_shared(B_hi)),
-                   "l"(src), "r"(bytes), "r"(mb[2 + s])
-                   : "memory");
-      // next X tile into the other buffer: its last reader (the A build of tile kt - 1) finished before the
-      // barrier that closed iteration kt - 1
-      if (kt + 1 < ktiles) fetch_x(kt + 1);
+  if (warp == 4) {
+    // ------------------------------------------------------------------ issuer
+    if (tid == 128) {
+      bulk(xs0, Xtile, xbytes, mb[7]);
+      if (ktiles > 1) bulk(xs0 + (size_t)D * FT_XS, Xtile + (size_t)D * FT_XS, xbytes, mb[8]);
+      bulk(Bslot, Wt + (size_t)ct * ktiles * bbytes, bbytes, mb[4]);
+      const uint64_t dA0 = ft_smem_desc((uint32_t)__cvta_generic_to_shared(Astage));
+      const uint64_t dB0 = ft_smem_desc((uint32_t)__cvta_generic_to_shared(Bslot));
+      constexpr uint64_t TILE16 = FT_TILE_BYTES >> 4;  // descriptor address units are 16 bytes
+      for (int j = 0; j < ktiles; ++j) {
+        const int s = j & 1, slot = j % 3;
+        ft_mbar_wait(mb[2 + s], (uint32_t)((j >> 1) & 1));   // A stage built (and X buffer s no longer read)
+        if (j + 2 < ktiles) bulk(xs0 + (size_t)s * D * FT_XS, Xtile + (size_t)(j + 2) * D * FT_XS, xbytes, mb[7 + s]);
+        ft_mbar_wait(mb[4 + slot], (uint32_t)((j / 3) & 1));  // B slot landed
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t a_hi = dA0 + (uint64_t)s * 2 * TILE16, a_lo = a_hi + TILE16;
+        const uint64_t b_hi = dB0 + (uint64_t)slot * 2 * TILE16, b_lo = b_hi + TILE16;
+        const int chunk = j / FT_KC;
+        const uint32_t td = tmem_d + (uint32_t)((chunk & 1) * FT_N);
+#pragma unroll
+        for (int k8 = 0; k8 < FT_KT / 8; ++k8) {
+          const uint64_t adv = (uint64_t)k8 * ((2u * FT_LBO) >> 4);  // one MMA consumes 8 tf32 = 2 core matrices along K
+          const uint32_t acc0 = ((j % FT_KC) > 0 || k8 > 0) ? 1u : 0u;
+          ft_mma(td, a_hi + adv, b_hi + adv, acc0);
+          ft_mma(td, a_hi + adv, b_lo + adv, 1u);
+          ft_mma(td, a_lo + adv, b_hi + adv, 1u);
+        }
+        // arrive when every MMA issued so far has finished reading shared memory / writing TMEM
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb[s]) : "memory");
+        if ((j % FT_KC) == FT_KC - 1 || j == ktiles - 1)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb[9 + (chunk & 1)]) : "memory");
+      }
     }
-    ft_mbar_wait(mb[6 + s], (uint32_t)(use & 1));  // X tile kt landed
-    // A stage: row = pair, z = x_i * x_j over the KT data rows
+  } else {
+    // ------------------------------------------------------------------ producers / drainers
+    int pi = 0, pj = 0;  // pair (i, j), i <= j, of row m0 + tid
     {
-      const float* xi = xs + (pi >= 0 ? pi : 0) * FT_KT;
-      const float* xj = xs + (pi >= 0 ? pj : 0) * FT_KT;
-#pragma unroll
-      for (int k4 = 0; k4 < FT_KT / 4; ++k4) {
-        const float4 a4 = *(const float4*)(xi + 4 * k4);
-        const float4 b4 = *(const float4*)(xj + 4 * k4);
-        float4 hi, lo;
-        const bool ok = pi >= 0;
-        ft_split(ok ? a4.x * b4.x : 0.f, hi.x, lo.x);
-        ft_split(ok ? a4.y * b4.y : 0.f, hi.y, lo.y);
-        ft_split(ok ? a4.z * b4.z : 0.f, hi.z, lo.z);
-        ft_split(ok ? a4.w * b4.w : 0.f, hi.w, lo.w);
-        const int off = (tid >> 3) * FT_SBO + k4 * FT_LBO + (tid & 7) * 16;
-        *(float4*)(A_hi + off) = hi;
-        *(float4*)(A_lo + off) = lo;
+      int m = m0 + tid;
+      if (m < P) {
+        int i = 0, rem = m;
+        while (rem >= D - i) { rem -= D - i; ++i; }
+        pi = i;
+        pj = i + rem;
+      } else {
+        pi = -1;
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      ft_mbar_wait(mb[2 + s], (uint32_t)(use & 1));  // B stage landed
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi_s = (uint32_t)__cvta_generic_to_shared(A_hi), a_lo_s = a_hi_s + FT_TILE_BYTES;
-      const uint32_t b_hi_s = a_lo_s + FT_TILE_BYTES, b_lo_s = b_hi_s + FT_TILE_BYTES;
-      const int chunk = kt / FT_KC;
-      const uint32_t td = tmem_d + (uint32_t)((chunk & 1) * FT_N);
+    // Two-level accumulation.  The tensor core adds partial products into TMEM with truncation, a
+    // bias that grows linearly with the number of accumulated K steps (measured: 2.3e-5 relative at
+    // N = 1000, 4.5e-5 at N = 2000).  Every FT_KC stages (128 data rows) the chunk is drained from TMEM
+    // and added to FP32 register accumulators with round-to-nearest; the next chunk restarts at zero.
+    float acc[FT_N];
 #pragma unroll
-      for (int k8 = 0; k8 < FT_KT / 8; ++k8) {
-        const uint32_t adv = (uint32_t)k8 * 2u * FT_LBO;  // one MMA consumes 8 tf32 = 2 core matrices along K
-        const uint32_t acc0 = ((kt % FT_KC) > 0 || k8 > 0) ? 1u : 0u;
-        ft_mma(td, ft_smem_desc(a_hi_s + adv), ft_smem_desc(b_hi_s + adv), acc0);
-        ft_mma(td, ft_smem_desc(a_hi_s + adv), ft_smem_desc(b_lo_s + adv), 1u);
-        ft_mma(td, ft_smem_desc(a_lo_s + adv), ft_smem_desc(b_hi_s + adv), 1u);
-      }
-      // arrives when every MMA issued so far has finished reading shared memory / writing TMEM
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb[s]) : "memory");
-      if ((kt % FT_KC) == FT_KC - 1 || kt == ktiles - 1)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb[4 + (chunk & 1)]) : "memory");
-    }
-    // first tile of a new chunk is in flight: drain the previous chunk's accumulator under it
-    if ((kt % FT_KC) == 0 && kt > 0) {
-      drain(kt / FT_KC - 1);
-      // (the __syncthreads of the following tiles order this drain before the accumulator's next overwrite,
-      //  which is issued FT_KC tiles later)
-    }
-  }
-  drain(nchunks - 1);
+    for (int e = 0; e < FT_N; ++e) acc[e] = 0.f;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 
-  // epilogue: registers -> G[c, i, j] (+ alpha on the diagonal)
-  if (pi >= 0) {
+    auto drain = [&](int chunk) {  // accumulator (chunk & 1) -> registers
+      ft_mbar_wait(mb[9 + (chunk & 1)], (uint32_t)((chunk >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t col0 = (uint32_t)((chunk & 1) * FT_N);
 #pragma unroll
-    for (int e = 0; e < FT_N; ++e) {
-      const long long c = c0 + e;
-      if (c < C) {
-        const float v = acc[e] + (pi == pj ? alpha : 0.f);
-        float* g = G + (size_t)c * D * D;
-        g[pi * D + pj] = v;
-        g[pj * D + pi] = v;
+      for (int col = 0; col < FT_N; col += 32) {
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(tmem_d + lane_base + col0 + (uint32_t)col));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[col + e] += __uint_as_float(r[e]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+
+    for (int kt = 0; kt < ktiles; ++kt) {
+      const int s = kt & 1, use = kt >> 1;
+      const float* xs = xs0 + (size_t)s * D * FT_XS;
+      unsigned char* A_hi = Astage + (size_t)s * 2 * FT_TILE_BYTES;
+      unsigned char* A_lo = A_hi + FT_TILE_BYTES;
+      if (kt >= 2) ft_mbar_wait(mb[s], (uint32_t)((use - 1) & 1));  // MMAs of tile kt - 2 done: A stage s, B slot (kt+1)%3 free
+      if (tid == 0 && kt + 1 < ktiles)
+        bulk(Bslot + (size_t)((kt + 1) % 3) * bbytes, Wt + ((size_t)ct * ktiles + kt + 1) * bbytes, bbytes, mb[4 + (kt + 1) % 3]);
+      ft_mbar_wait(mb[7 + s], (uint32_t)(use & 1));  // X tile kt landed
+      {
+        const float* xi = xs + (pi >= 0 ? pi : 0) * FT_XS;
+        const float* xj = xs + (pi >= 0 ? pj : 0) * FT_XS;
+        const bool ok = pi >= 0;
+#pragma unroll
+        for (int k4 = 0; k4 < FT_KT / 4; ++k4) {
+          const float4 a4 = *(const float4*)(xi + 4 * k4);
+          const float4 b4 = *(const float4*)(xj + 4 * k4);
+          float4 hi, lo;
+          ft_split(ok ? a4.x * b4.x : 0.f, hi.x, lo.x);
+          ft_split(ok ? a4.y * b4.y : 0.f, hi.y, lo.y);
+          ft_split(ok ? a4.z * b4.z : 0.f, hi.z, lo.z);
+          ft_split(ok ? a4.w * b4.w : 0.f, hi.w, lo.w);
+          const int off = (tid >> 3) * FT_SBO + k4 * FT_LBO + (tid & 7) * 16;
+          *(float4*)(A_hi + off) = hi;
+          *(float4*)(A_lo + off) = lo;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb[2 + s]) : "memory");
+      // the first tile of a new chunk is queued: drain the previous chunk's accumulator under it.  This thread
+      // arrives for a later tile only after its drain, and the accumulator's next overwrite is issued FT_KC
+      // tiles later, after every producer arrived for that tile.
+      if ((kt % FT_KC) == 0 && kt > 0) drain(kt / FT_KC - 1);
+    }
+    drain(nchunks - 1);
+
+    // epilogue: registers -> G[c, i, j] (+ alpha on the diagonal)
+    if (pi >= 0) {
+#pragma unroll
+      for (int e = 0; e < FT_N; ++e) {
+        const long long c = c0 + e;
+        if (c < C) {
+          const float v = acc[e] + (pi == pj ? alpha : 0.f);
+          float* g = G + (size_t)c * D * D;
+          g[pi * D + pj] = v;
+          g[pj * D + pi] = v;
+        }
       }
     }
   }
@@ -325,7 +332,7 @@ extern "C" int gb200_logreg_fisher_metric(const gb200_target_desc* t, const void
   const int ktiles = (N + FT_KT - 1) / FT_KT;
   const long long ctiles = (C + FT_N - 1) / FT_N;
   const int64_t wt_bytes = (int64_t)ctiles * ktiles * 2 * FT_TILE_BYTES;
-  const int64_t need = wt_bytes + (int64_t)ktiles * D * FT_KT * 4;
+  const int64_t need = wt_bytes + (int64_t)ktiles * D * FT_XS * 4;
   if (workspace_bytes < need) { set_error("fisher_metric: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)need); return GB200_ERR_INVALID_ARGUMENT; }
   if (ldx % 4 != 0 || ((uintptr_t)workspace & 15) != 0) { set_error("fisher_metric: ldx must be a multiple of 4 and the workspace 16-byte aligned"); return GB200_ERR_INVALID_ARGUMENT; }
   cudaStream_t s = (cudaStream_t)stream;
@@ -337,12 +344,12 @@ extern "C" int gb200_logreg_fisher_metric(const gb200_target_desc* t, const void
   }
   float* Xtile = (float*)(Wt + wt_bytes);
   {
-    const long long total = (long long)ktiles * D * FT_KT;
+    const long long total = (long long)ktiles * D * FT_XS;
     fisher_xtile_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float*)t->vec0, ldx, N, D, Xtile, ktiles);
     GB_CHECK_LAUNCH();
   }
   const int P = D * (D + 1) / 2;
-  const size_t smem = 8 * FT_TILE_BYTES + 2 * (size_t)D * FT_KT * 4 + 1024;
+  const size_t smem = 10 * FT_TILE_BYTES + 2 * (size_t)D * FT_XS * 4 + 1024;
   cudaError_t e = cudaFuncSetAttribute(fisher_metric_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("fisher_metric: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
   dim3 grid((unsigned)((P + FT_M - 1) / FT_M), (unsigned)ctiles);
@@ -356,5 +363,5 @@ extern "C" int64_t gb200_logreg_fisher_metric_workspace(const gb200_target_desc*
   const int64_t ktiles = ((int64_t)t->N + FT_KT - 1) / FT_KT;
   const int64_t ctiles = (C + FT_N - 1) / FT_N;
   // pre-split W^T tiles (hi + lo), see fisher_weights_kernel, + the re-tiled X (fisher_xtile_kernel)
-  return ctiles * ktiles * 2 * FT_TILE_BYTES + ktiles * (int64_t)t->D * FT_KT * 4;
+  return ctiles * ktiles * 2 * FT_TILE_BYTES + ktiles * (int64_t)t->D * FT_XS * 4;
 }
