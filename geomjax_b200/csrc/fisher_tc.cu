@@ -22,7 +22,7 @@ constexpr int FT_M = 128;      // pairs per CTA (MMA M)
 constexpr int FT_N = 128;      // chains per CTA (MMA N)
 constexpr int FT_KT = 32;      // data rows per stage
 constexpr int FT_KC = 4;       // stages per TMEM accumulation chunk (see the epilogue note)
-constexpr int FT_THREADS = 160;  // warps 0-3: operand producers + accumulator drainers; warp 4: TMA / MMA issuer
+constexpr int FT_THREADS = 288;  // warps 0-7: operand producers + accumulator drainers (2 threads per pair row); warp 8: TMA / MMA issuer
 constexpr int FT_XS = FT_KT + 4;  // padded row stride (floats) of the staged X tile: conflict-free float4 row reads
 constexpr int FT_LBO = 128;                  // bytes
 constexpr int FT_SBO = (FT_KT / 4) * 128;    // bytes
@@ -123,13 +123,14 @@ __device__ __forceinline__ void ft_mbar_wait(uint32_t mbar_a, uint32_t parity) {
 }
 
 // ---- the GEMM: warp-specialised, two A stages, three B slots, two TMEM accumulators -----------------------
-// Producers (warps 0-3, thread = pair row = TMEM lane), per K tile kt (32 data rows):
+// Producers (warps 0-7; thread pair = pair row = TMEM lane, each thread half of the K range and half of the
+// accumulator columns), per K tile kt (32 data rows):
 //   wait until the MMAs of tile kt-2 are done (A stage kt&1 and B slot (kt+1)%3 are free); thread 0 starts the
 //   bulk copy of B(kt+1); wait for the X tile (bulk-copied two tiles ahead by the issuer); build the Khatri-Rao
 //   A stage (z = x_i x_j, split into TF32 hi / lo) and ARRIVE on the stage's mbarrier -- no block-wide barrier.
 //   On the first tile of a chunk they then drain the previous chunk's TMEM accumulator into FP32 registers
 //   (two-level accumulation, see below) while the tensor core already works on the new chunk.
-// Issuer (warp 4, one lane): waits for "A built" + "B landed", issues the 12 MMAs (3xTF32 x 4 K-steps) from
+// Issuer (warp 8, one lane): waits for "A built" + "B landed", issues the 12 MMAs (3xTF32 x 4 K-steps) from
 //   pre-built descriptors, commits to the stage's "free" mbarrier (and the accumulator's "complete" mbarrier at
 //   a chunk end), and refills the X buffer the producers just finished with.
 __global__ void __launch_bounds__(FT_THREADS, 1)
@@ -164,7 +165,7 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 11; ++i) {
-      const uint32_t cnt = (i == 2 || i == 3) ? 128u : 1u;  // "built": every producer thread arrives
+      const uint32_t cnt = (i == 2 || i == 3) ? 256u : 1u;  // "built": every producer thread arrives
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb[i]), "r"(cnt));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,9 +183,9 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
                  : "memory");
   };
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ issuer
-    if (tid == 128) {
+    if (tid == 256) {
       bulk(xs0, Xtile, xbytes, mb[7]);
       if (ktiles > 1) bulk(xs0 + (size_t)D * FT_XS, Xtile + (size_t)D * FT_XS, xbytes, mb[8]);
       bulk(Bslot, Wt + (size_t)ct * ktiles * bbytes, bbytes, mb[4]);
@@ -217,9 +218,10 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
     }
   } else {
     // ------------------------------------------------------------------ producers / drainers
-    int pi = 0, pj = 0;  // pair (i, j), i <= j, of row m0 + tid
+    const int row = tid & 127, half = tid >> 7;
+    int pi = 0, pj = 0;  // pair (i, j), i <= j, of row m0 + row
     {
-      int m = m0 + tid;
+      int m = m0 + row;
       if (m < P) {
         int i = 0, rem = m;
         while (rem >= D - i) { rem -= D - i; ++i; }
@@ -233,17 +235,18 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
     // bias that grows linearly with the number of accumulated K steps (measured: 2.3e-5 relative at
     // N = 1000, 4.5e-5 at N = 2000).  Every FT_KC stages (128 data rows) the chunk is drained from TMEM
     // and added to FP32 register accumulators with round-to-nearest; the next chunk restarts at zero.
-    float acc[FT_N];
+    constexpr int NH = FT_N / 2;  // accumulator columns (chains) owned by this thread
+    float acc[NH];
 #pragma unroll
-    for (int e = 0; e < FT_N; ++e) acc[e] = 0.f;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int e = 0; e < NH; ++e) acc[e] = 0.f;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;  // warp w may access TMEM lanes 32 (w % 4) ..
 
     auto drain = [&](int chunk) {  // accumulator (chunk & 1) -> registers
       ft_mbar_wait(mb[9 + (chunk & 1)], (uint32_t)((chunk >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t col0 = (uint32_t)((chunk & 1) * FT_N);
+      const uint32_t col0 = (uint32_t)((chunk & 1) * FT_N + half * NH);
 #pragma unroll
-      for (int col = 0; col < FT_N; col += 32) {
+      for (int col = 0; col < NH; col += 32) {
         uint32_t r[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -275,7 +278,8 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
         const float* xj = xs + (pi >= 0 ? pj : 0) * FT_XS;
         const bool ok = pi >= 0;
 #pragma unroll
-        for (int k4 = 0; k4 < FT_KT / 4; ++k4) {
+        for (int kq = 0; kq < FT_KT / 8; ++kq) {
+          const int k4 = half * (FT_KT / 8) + kq;
           const float4 a4 = *(const float4*)(xi + 4 * k4);
           const float4 b4 = *(const float4*)(xj + 4 * k4);
           float4 hi, lo;
@@ -283,7 +287,7 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
           ft_split(ok ? a4.y * b4.y : 0.f, hi.y, lo.y);
           ft_split(ok ? a4.z * b4.z : 0.f, hi.z, lo.z);
           ft_split(ok ? a4.w * b4.w : 0.f, hi.w, lo.w);
-          const int off = (tid >> 3) * FT_SBO + k4 * FT_LBO + (tid & 7) * 16;
+          const int off = (row >> 3) * FT_SBO + k4 * FT_LBO + (row & 7) * 16;
           *(float4*)(A_hi + off) = hi;
           *(float4*)(A_lo + off) = lo;
         }
@@ -300,8 +304,8 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
     // epilogue: registers -> G[c, i, j] (+ alpha on the diagonal)
     if (pi >= 0) {
 #pragma unroll
-      for (int e = 0; e < FT_N; ++e) {
-        const long long c = c0 + e;
+      for (int e = 0; e < NH; ++e) {
+        const long long c = c0 + half * NH + e;
         if (c < C) {
           const float v = acc[e] + (pi == pj ? alpha : 0.f);
           float* g = G + (size_t)c * D * D;
