@@ -96,6 +96,8 @@ PROTOTYPES = {
     "gb200_ess_finalize": (C.c_int, [_P(_dbl), _P(_dbl), _i64, _i64, _i32, _i32, _P(_dbl), _P(C.c_uint8)]),
     "gb200_logreg_fisher_metric": (C.c_int, [_P(TargetDesc), vp, vp, vp, _i64, _i64, _i32, vp]),
     "gb200_logreg_fisher_metric_workspace": (_i64, [_P(TargetDesc), _i64]),
+    "gb200_logreg_quadform": (C.c_int, [_P(TargetDesc), vp, vp, _i64, vp, _i64, _i64, _i32, vp]),
+    "gb200_logreg_quadform_workspace": (_i64, [_P(TargetDesc), _i64]),
     "gb200_fp32_peak_kernel": (C.c_int, [vp, _i32, _i32, _i64, vp]),
     "gb200_flops_per_chain_step": (_dbl, [_i32, _P(TargetDesc)]),
     "gb200_flops_per_transition": (_dbl, [_i32, _P(TargetDesc)]),

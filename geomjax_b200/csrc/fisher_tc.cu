@@ -133,9 +133,15 @@ __device__ __forceinline__ void ft_mbar_wait(uint32_t mbar_a, uint32_t parity) {
 // Issuer (warp 8, one lane): waits for "A built" + "B landed", issues the 12 MMAs (3xTF32 x 4 K-steps) from
 //   pre-built descriptors, commits to the stage's "free" mbarrier (and the accumulator's "complete" mbarrier at
 //   a chunk end), and refills the X buffer the producers just finished with.
+// QUAD = false: vec(G)[pair, chain] = sum_n Z[n, pair] w[n, chain]   (M = pairs, K = data rows; A from X tiles)
+// QUAD = true : h[n, chain] = sum_pair Z[n, pair] B[pair, chain]       (M = data rows, K = pairs; the 128 data rows
+//               of the CTA are staged ONCE, the pair list comes from a table; B = m_pair * A_c[i, j] pre-tiled):
+//               the quadratic forms x_n^T A_c x_n of rmhmc's dT/dq on the same pipeline.
+template <bool QUAD>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const unsigned char* __restrict__ Wt,
-                        long long C, float alpha, float* __restrict__ G) {
+                        long long C, float alpha, float* __restrict__ G,
+                        const float* __restrict__ Xt, int ldx, const short2* __restrict__ pairs, int PS, int ldh) {
   extern __shared__ __align__(1024) unsigned char ft_smem[];
   unsigned char* Astage = ft_smem;                                  // 2 x [A_hi | A_lo]
   unsigned char* Bslot = ft_smem + 2 * 2 * FT_TILE_BYTES;           // 3 x [B_hi | B_lo] (one bulk copy each)
@@ -153,8 +159,17 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
   for (int i = 0; i < 11; ++i) mb[i] = (uint32_t)__cvta_generic_to_shared(&mbar[i]);
   const uint32_t xbytes = (uint32_t)D * FT_XS * 4;
   const uint32_t bbytes = 2 * FT_TILE_BYTES;
-  const int ktiles = (N + FT_KT - 1) / FT_KT;
+  const int ktiles = QUAD ? PS / FT_KT : (N + FT_KT - 1) / FT_KT;
   const int nchunks = (ktiles + FT_KC - 1) / FT_KC;
+  const int DX = D | 1;  // QUAD: odd row stride of the staged data rows xr[128][DX] (lanes = rows: conflict-free)
+  if (QUAD) {
+    float* xr = xs0;
+    for (int e = tid; e < FT_M * D; e += FT_THREADS) {
+      const int i = e / FT_M, r = e - i * FT_M;
+      const int n = m0 + r;
+      xr[r * DX + i] = (n < N) ? Xt[(size_t)i * ldx + n] : 0.f;
+    }
+  }
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -186,8 +201,10 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
   if (warp == 8) {
     // ------------------------------------------------------------------ issuer
     if (tid == 256) {
-      bulk(xs0, Xtile, xbytes, mb[7]);
-      if (ktiles > 1) bulk(xs0 + (size_t)D * FT_XS, Xtile + (size_t)D * FT_XS, xbytes, mb[8]);
+      if (!QUAD) {
+        bulk(xs0, Xtile, xbytes, mb[7]);
+        if (ktiles > 1) bulk(xs0 + (size_t)D * FT_XS, Xtile + (size_t)D * FT_XS, xbytes, mb[8]);
+      }
       bulk(Bslot, Wt + (size_t)ct * ktiles * bbytes, bbytes, mb[4]);
       const uint64_t dA0 = ft_smem_desc((uint32_t)__cvta_generic_to_shared(Astage));
       const uint64_t dB0 = ft_smem_desc((uint32_t)__cvta_generic_to_shared(Bslot));
@@ -195,7 +212,7 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
       for (int j = 0; j < ktiles; ++j) {
         const int s = j & 1, slot = j % 3;
         ft_mbar_wait(mb[2 + s], (uint32_t)((j >> 1) & 1));   // A stage built (and X buffer s no longer read)
-        if (j + 2 < ktiles) bulk(xs0 + (size_t)s * D * FT_XS, Xtile + (size_t)(j + 2) * D * FT_XS, xbytes, mb[7 + s]);
+        if (!QUAD && j + 2 < ktiles) bulk(xs0 + (size_t)s * D * FT_XS, Xtile + (size_t)(j + 2) * D * FT_XS, xbytes, mb[7 + s]);
         ft_mbar_wait(mb[4 + slot], (uint32_t)((j / 3) & 1));  // B slot landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t a_hi = dA0 + (uint64_t)s * 2 * TILE16, a_lo = a_hi + TILE16;
@@ -220,7 +237,7 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
     // ------------------------------------------------------------------ producers / drainers
     const int row = tid & 127, half = tid >> 7;
     int pi = 0, pj = 0;  // pair (i, j), i <= j, of row m0 + row
-    {
+    if (!QUAD) {
       int m = m0 + row;
       if (m < P) {
         int i = 0, rem = m;
@@ -272,6 +289,26 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
       if (kt >= 2) ft_mbar_wait(mb[s], (uint32_t)((use - 1) & 1));  // MMAs of tile kt - 2 done: A stage s, B slot (kt+1)%3 free
       if (tid == 0 && kt + 1 < ktiles)
         bulk(Bslot + (size_t)((kt + 1) % 3) * bbytes, Wt + ((size_t)ct * ktiles + kt + 1) * bbytes, bbytes, mb[4 + (kt + 1) % 3]);
+      if (QUAD) {
+        // A stage: row = data row, z = x_i x_j over the 32 pairs of this K tile (pair list is warp-uniform)
+        const float* xrow = xs0 + row * DX;
+#pragma unroll
+        for (int kq = 0; kq < FT_KT / 8; ++kq) {
+          const int k4 = half * (FT_KT / 8) + kq;
+          const short2* pp = pairs + kt * FT_KT + 4 * k4;
+          float z[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const short2 ij = __ldg(pp + e);
+            z[e] = xrow[ij.x] * xrow[ij.y];  // padded pairs point at (0, 0) and meet zero rows of B
+          }
+          float4 hi, lo;
+          ft_split(z[0], hi.x, lo.x); ft_split(z[1], hi.y, lo.y); ft_split(z[2], hi.z, lo.z); ft_split(z[3], hi.w, lo.w);
+          const int off = (row >> 3) * FT_SBO + k4 * FT_LBO + (row & 7) * 16;
+          *(float4*)(A_hi + off) = hi;
+          *(float4*)(A_lo + off) = lo;
+        }
+      } else {
       ft_mbar_wait(mb[7 + s], (uint32_t)(use & 1));  // X tile kt landed
       {
         const float* xi = xs + (pi >= 0 ? pi : 0) * FT_XS;
@@ -292,6 +329,7 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
           *(float4*)(A_lo + off) = lo;
         }
       }
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb[2 + s]) : "memory");
       // the first tile of a new chunk is queued: drain the previous chunk's accumulator under it.  This thread
@@ -301,8 +339,18 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
     }
     drain(nchunks - 1);
 
-    // epilogue: registers -> G[c, i, j] (+ alpha on the diagonal)
-    if (pi >= 0) {
+    if (QUAD) {
+      // epilogue: registers -> h[c, n] (chain-major rows of length ldh; lanes = consecutive data rows: coalesced)
+      const int n = m0 + row;
+      if (n < N) {
+#pragma unroll
+        for (int e = 0; e < NH; ++e) {
+          const long long c = c0 + half * NH + e;
+          if (c < C) G[(size_t)c * ldh + n] = acc[e];
+        }
+      }
+    } else if (pi >= 0) {
+      // epilogue: registers -> G[c, i, j] (+ alpha on the diagonal)
 #pragma unroll
       for (int e = 0; e < NH; ++e) {
         const long long c = c0 + half * NH + e;
@@ -354,10 +402,105 @@ extern "C" int gb200_logreg_fisher_metric(const gb200_target_desc* t, const void
   }
   const int P = D * (D + 1) / 2;
   const size_t smem = 10 * FT_TILE_BYTES + 2 * (size_t)D * FT_XS * 4 + 1024;
-  cudaError_t e = cudaFuncSetAttribute(fisher_metric_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(fisher_metric_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("fisher_metric: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
   dim3 grid((unsigned)((P + FT_M - 1) / FT_M), (unsigned)ctiles);
-  fisher_metric_tc_kernel<<<grid, FT_THREADS, smem, s>>>(Xtile, N, D, Wt, C, (float)t->params[0], (float*)metric);
+  fisher_metric_tc_kernel<false><<<grid, FT_THREADS, smem, s>>>(Xtile, N, D, Wt, C, (float)t->params[0], (float*)metric,
+                                                               nullptr, 0, nullptr, 0, 0);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+
+// ---- quadratic forms h[c, n] = x_n^T A_c x_n for symmetric per-chain matrices A_c [C, D, D] ------------------
+namespace gb {
+__global__ void quadform_pairs_kernel(short2* pairs, int D, int P, int PS) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= PS) return;
+  int i = 0, rem = p;
+  if (p < P) {
+    while (rem >= D - i) { rem -= D - i; ++i; }
+    pairs[p] = make_short2((short)i, (short)(i + rem));
+  } else {
+    pairs[p] = make_short2(0, 0);
+  }
+}
+// B operand: row = chain, k = pair; value = A_c[i, j] (x 2 off the diagonal), TF32 hi / lo, UMMA tile layout
+// (same thread -> address map as fisher_weights_kernel: 64 consecutive threads write one contiguous 1 KB group).
+__global__ void __launch_bounds__(256)
+quadform_b_kernel(const float* __restrict__ A, int D, int P, const short2* __restrict__ pairs, long long C,
+                  unsigned char* __restrict__ Bt, int ktiles, long long ctiles) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long tile = gid >> 10;
+  if (tile >= ctiles * ktiles) return;
+  const int l = (int)(gid & 1023);
+  const int rg = l >> 6, row = rg * 8 + (l & 7), kq = (l >> 3) & 7;
+  const long long ct = tile / ktiles;
+  const int kt = (int)(tile - ct * ktiles);
+  const long long c = ct * FT_N + row;
+  float w[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    const float* Ac = A + (size_t)c * D * D;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int p = kt * FT_KT + 4 * kq + e;
+      if (p < P) {
+        const short2 ij = pairs[p];
+        w[e] = Ac[ij.x * D + ij.y] * (ij.x == ij.y ? 1.f : 2.f);
+      }
+    }
+  }
+  float4 hi, lo;
+  ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
+  unsigned char* base = Bt + (size_t)tile * (2 * FT_TILE_BYTES) + (size_t)rg * FT_SBO + kq * FT_LBO + (l & 7) * 16;
+  *(float4*)base = hi;
+  *(float4*)(base + FT_TILE_BYTES) = lo;
+}
+}  // namespace gb
+
+static int64_t quadform_ws(int D, int64_t C, int64_t* bt_bytes, int* PS_out) {
+  const int P = D * (D + 1) / 2;
+  const int PS = (P + FT_KT - 1) / FT_KT * FT_KT;
+  const int64_t ctiles = (C + FT_N - 1) / FT_N;
+  const int64_t bt = ctiles * (PS / FT_KT) * 2 * FT_TILE_BYTES;
+  if (bt_bytes) *bt_bytes = bt;
+  if (PS_out) *PS_out = PS;
+  return bt + (int64_t)PS * sizeof(short2);
+}
+
+extern "C" int64_t gb200_logreg_quadform_workspace(const gb200_target_desc* t, int64_t C) {
+  return t ? quadform_ws(t->D, C, nullptr, nullptr) : 0;
+}
+
+extern "C" int gb200_logreg_quadform(const gb200_target_desc* t, const void* matrices, void* h, int64_t ldh, void* workspace,
+                                     int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream) {
+  if (!t || t->kind != GB200_TARGET_LOGREG) { set_error("quadform: needs a logistic-regression target"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (dtype != GB200_F32) { set_error("quadform: float32 only"); return GB200_ERR_UNSUPPORTED; }
+  if (C == 0) return GB200_OK;
+  const int N = (int)t->N, D = t->D, ldx = (int)t->params[1];
+  if (!matrices || !h || !workspace || C < 0 || !t->vec0 || ldh < N) { set_error("quadform: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
+  int64_t bt_bytes;
+  int PS;
+  const int64_t need = quadform_ws(D, C, &bt_bytes, &PS);
+  if (workspace_bytes < need || ((uintptr_t)workspace & 15) != 0) { set_error("quadform: workspace too small or not 16-byte aligned (%lld < %lld bytes)", (long long)workspace_bytes, (long long)need); return GB200_ERR_INVALID_ARGUMENT; }
+  const int P = D * (D + 1) / 2, ktiles = PS / FT_KT;
+  const long long ctiles = (C + FT_N - 1) / FT_N;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char* Bt = (unsigned char*)workspace;
+  short2* pairs = (short2*)(Bt + bt_bytes);
+  quadform_pairs_kernel<<<(PS + 255) / 256, 256, 0, s>>>(pairs, D, P, PS);
+  GB_CHECK_LAUNCH();
+  {
+    const long long total = ctiles * ktiles * 1024;
+    quadform_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float*)matrices, D, P, pairs, C, Bt, ktiles, ctiles);
+    GB_CHECK_LAUNCH();
+  }
+  const size_t smem = 10 * FT_TILE_BYTES + (size_t)FT_M * (D | 1) * 4 + 1024;
+  if (smem > 227 * 1024) { set_error("quadform: D=%d does not fit the staged data-row tile", D); return GB200_ERR_UNSUPPORTED; }
+  cudaError_t e = cudaFuncSetAttribute(fisher_metric_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("quadform: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
+  dim3 grid((unsigned)((N + FT_M - 1) / FT_M), (unsigned)ctiles);
+  fisher_metric_tc_kernel<true><<<grid, FT_THREADS, smem, s>>>(nullptr, N, D, Bt, C, 0.f, (float*)h, (const float*)t->vec0, ldx,
+                                                              pairs, PS, (int)ldh);
   GB_CHECK_LAUNCH();
   return GB200_OK;
 }

@@ -48,6 +48,26 @@ class TargetDescriptor:
                                                        q.shape[0], N.F32, N.stream_ptr()))
         return G
 
+    def quadratic_forms(self, matrices):
+        """``h[c, n] = x_n^T A_c x_n`` for per-chain symmetric matrices ``A`` (C, D, D) -> (C, N): with ``A = G^-1``
+        the ``h_n`` of rmhmc's ``dT/dq`` on the logistic-regression target, as one tcgen05 (3xTF32) GEMM over the
+        chain dimension (the twin of ``evaluate_metric``)."""
+        import ctypes as C
+        import torch
+        if self.kind != N.TARGET_LOGREG:
+            raise NotImplementedError("quadratic_forms() is built for the logistic-regression target")
+        A = matrices.to(torch.float32).contiguous()
+        if A.ndim != 3 or A.shape[1:] != (self.D, self.D):
+            raise ValueError(f"matrices must have shape (C, {self.D}, {self.D})")
+        d = self.c_struct()
+        ws_bytes = N.lib().gb200_logreg_quadform_workspace(C.byref(d), A.shape[0])
+        ws = torch.empty(max(int(ws_bytes), 16) // 4, dtype=torch.float32, device=A.device)
+        h = torch.empty((A.shape[0], self.N), dtype=torch.float32, device=A.device)
+        with torch.cuda.device(A.device):
+            N.check(N.lib().gb200_logreg_quadform(C.byref(d), N.ptr(A), N.ptr(h), self.N, N.ptr(ws), ws_bytes,
+                                                  A.shape[0], N.F32, N.stream_ptr()))
+        return h
+
     def with_metric(self, metric: str) -> "TargetDescriptor":
         """``metric='identity'`` == ``metric_fn=lambda x: jnp.eye(D)`` (tests/test_samplers.py:25)."""
         m = {"target": N.METRIC_TARGET, "identity": N.METRIC_IDENTITY}[metric]

@@ -228,6 +228,12 @@ int gb200_ess_finalize(const double* acov_host, const double* rhat_stats_host, i
 int gb200_logreg_fisher_metric(const gb200_target_desc* target, const void* position, void* metric, void* workspace,
                                int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream);
 int64_t gb200_logreg_fisher_metric_workspace(const gb200_target_desc* target, int64_t C);
+/* h[c, n] = x_n^T A_c x_n for per-chain symmetric matrices A[C, D, D] (e.g. A = G^-1: the h_n of rmhmc's
+ * dT/dq_i = 1/2 sum_n w'_n x_ni (h_n - u_n^2), SURVEY Appendix B.1 GEMM 5) as ONE tcgen05 (3xTF32) GEMM
+ * h[N, C] = Z[N, P] . vecsym(A)[P, C] over the chain dimension.  h is [C, ldh] float32, ldh >= N. */
+int gb200_logreg_quadform(const gb200_target_desc* target, const void* matrices, void* h, int64_t ldh, void* workspace,
+                          int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream);
+int64_t gb200_logreg_quadform_workspace(const gb200_target_desc* target, int64_t C);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Runs a dependent-FMA microbenchmark (iters FFMA per thread on grid x block threads) for the FP32

@@ -126,3 +126,23 @@ def test_step_size_adaptation_on_logreg(cuda, Nrows, D):
     alg = g.rmhmc(target, eps, target, 2)
     st, i2 = alg.step(g.random.chain_keys(g.random.PRNGKey(9), 0, 1, C), res.state)
     assert bool(torch.isfinite(st.position).all())
+
+
+@pytest.mark.parametrize("Nrows,D,C", [(1000, 25, 300), (70, 4, 7), (333, 17, 129), (10000, 100, 130)])
+def test_quadratic_forms_tcgen05_vs_float64(cuda, Nrows, D, C):
+    """h[c, n] = x_n^T A_c x_n (GEMM 5 of SURVEY Appendix B.1) on the warp-specialised tcgen05 pipeline vs
+    float64 NumPy, with A_c = the inverse Fisher metric of random positions; error at FP32 level."""
+    import geomjax_b200 as g
+    X, y = T.make_logreg_data(Nrows, D, seed=2)
+    t64 = T.LogisticRegression(X.astype(np.float64), y.astype(np.float64), 0.01, dtype=np.float64)
+    q = (0.3 * np.random.default_rng(C).standard_normal((C, D)))
+    A = np.linalg.inv(t64.metric(q))
+    A = 0.5 * (A + A.transpose(0, 2, 1))
+    want = np.einsum("ni,cij,nj->cn", X.astype(np.float64), A, X.astype(np.float64), optimize=True)
+    target = g.logistic_regression(_t(X, cuda), _t(y, cuda), 0.01)
+    got = target.quadratic_forms(_t(A.astype(np.float32), cuda)).cpu().numpy()
+    A32 = A.astype(np.float32).astype(np.float64)  # the kernel sees the float32-rounded matrices
+    want32 = np.einsum("ni,cij,nj->cn", X.astype(np.float64), A32, X.astype(np.float64), optimize=True)
+    scale = np.abs(want).max(axis=1, keepdims=True)
+    err = np.abs(got - want32) / scale
+    assert err.max() < 5e-6, err.max()
