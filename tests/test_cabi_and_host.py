@@ -111,3 +111,22 @@ def test_build_schedule_matches_reference_shape():
     assert build_schedule(10) == [(0, False)] * 10
     s = build_schedule(100)
     assert len(s) == 100 and [i for i, (_, e) in enumerate(s) if e] == [89]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle port the driver times beside the GPU arm) prints ONE JSON
+    line with the contract's keys; it must run without a GPU."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=240, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "chain-leapfrog-steps/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["unit"] == "chain-steps/s" and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and line["gpu_launches"] == 0
