@@ -66,7 +66,8 @@ __device__ __forceinline__ void ft_split(float a, float& hi, float& lo) {
 // = one 16-byte core-matrix row; 64 consecutive threads write one contiguous 1 KB row group.
 __global__ void __launch_bounds__(256)
 fisher_weights_kernel(const float* __restrict__ Xt, int ldx, int N, int D, const float* __restrict__ theta,
-                      long long C, unsigned char* __restrict__ Wt, int ktiles, long long ctiles) {
+                      long long C, unsigned char* __restrict__ Wt, int ktiles, long long ctiles,
+                      float* __restrict__ eta_out, long long ld_eta) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long tile = gid >> 10;  // 1024 threads per (chain tile, K tile): 128 rows x 8 k-quads
   if (tile >= ctiles * ktiles) return;
@@ -91,6 +92,7 @@ fisher_weights_kernel(const float* __restrict__ Xt, int ldx, int N, int D, const
       const float sg = 1.f / (1.f + expf(-eta[e]));
       w[e] = (n + e < N) ? sg * (1.f - sg) : 0.f;
     }
+    if (eta_out != nullptr) *(float4*)(eta_out + c * ld_eta + n) = make_float4(eta[0], eta[1], eta[2], eta[3]);
   }
   float4 hi, lo;
   ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
@@ -374,8 +376,17 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
 
 using namespace gb;
 
+namespace gb {
+int fisher_metric_launch(const gb200_target_desc* t, const void* position, void* metric, void* workspace,
+                         int64_t workspace_bytes, int64_t C, int32_t dtype, float* eta_out, long long ld_eta, void* stream);
+}
 extern "C" int gb200_logreg_fisher_metric(const gb200_target_desc* t, const void* position, void* metric, void* workspace,
                                           int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream) {
+  return gb::fisher_metric_launch(t, position, metric, workspace, workspace_bytes, C, dtype, nullptr, 0, stream);
+}
+// eta_out (optional): eta[c, n] = x_n . theta_c, row stride ld_eta (multiple of 4, >= N rounded up to 4)
+int gb::fisher_metric_launch(const gb200_target_desc* t, const void* position, void* metric, void* workspace,
+                             int64_t workspace_bytes, int64_t C, int32_t dtype, float* eta_out, long long ld_eta, void* stream) {
   if (!t || t->kind != GB200_TARGET_LOGREG) { set_error("fisher_metric: needs a logistic-regression target"); return GB200_ERR_INVALID_ARGUMENT; }
   if (dtype != GB200_F32) { set_error("fisher_metric: float32 only"); return GB200_ERR_UNSUPPORTED; }
   if (C == 0) return GB200_OK;
@@ -391,7 +402,7 @@ extern "C" int gb200_logreg_fisher_metric(const gb200_target_desc* t, const void
   unsigned char* Wt = (unsigned char*)workspace;
   {
     const long long total = ctiles * ktiles * 1024;
-    fisher_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float*)t->vec0, ldx, N, D, (const float*)position, C, Wt, ktiles, ctiles);
+    fisher_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float*)t->vec0, ldx, N, D, (const float*)position, C, Wt, ktiles, ctiles, eta_out, ld_eta);
     GB_CHECK_LAUNCH();
   }
   float* Xtile = (float*)(Wt + wt_bytes);

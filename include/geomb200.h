@@ -234,6 +234,16 @@ int64_t gb200_logreg_fisher_metric_workspace(const gb200_target_desc* target, in
 int gb200_logreg_quadform(const gb200_target_desc* target, const void* matrices, void* h, int64_t ldh, void* workspace,
                           int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream);
 int64_t gb200_logreg_quadform_workspace(const gb200_target_desc* target, int64_t C);
+/* ONE evaluation of rmhmc's implicit-midpoint map (rmhmc/integrators.py:119-142) for ALL chains in lock-step on the
+ * logistic-regression target, both D^2 N products on the tcgen05 GEMMs above:
+ *   (qn, pn) = (qi + h dH/dp(q, p), pi - h dH/dq(q, p)),  h = half_step,
+ *   dH/dp = G(q)^-1 p (-> velocity),  dH/dq = dT/dq - grad logp  (-> logdensity, logdensity_grad, logdet G, dTdq).
+ * All arrays [C, D] / [C] float32; dTdq may be NULL.  The unit a lock-step fixed-point loop repeats. */
+int gb200_logreg_midpoint_map(const gb200_target_desc* target, const void* q, const void* p, const void* qi, const void* pi,
+                              double half_step, void* qn, void* pn, void* logdensity, void* logdensity_grad, void* velocity,
+                              void* logdet, void* dTdq, void* workspace, int64_t workspace_bytes, int64_t C, int32_t dtype,
+                              void* stream);
+int64_t gb200_logreg_midpoint_map_workspace(const gb200_target_desc* target, int64_t C);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Runs a dependent-FMA microbenchmark (iters FFMA per thread on grid x block threads) for the FP32

@@ -146,3 +146,39 @@ def test_quadratic_forms_tcgen05_vs_float64(cuda, Nrows, D, C):
     scale = np.abs(want).max(axis=1, keepdims=True)
     err = np.abs(got - want32) / scale
     assert err.max() < 5e-6, err.max()
+
+
+@pytest.mark.parametrize("Nrows,D,C", [(200, 8, 40), (1000, 25, 130), (10000, 100, 6)])
+def test_lockstep_midpoint_map_vs_oracle(cuda, Nrows, D, C):
+    """One evaluation of the implicit-midpoint map for all chains at once, both D^2 N products on the tcgen05
+    GEMMs (the unit of a lock-step fixed-point loop), against the oracle's dense evaluation
+    (rmhmc/integrators.py:119-142 via oracle.samplers._rmhmc_kinetic_grad)."""
+    import geomjax_b200 as g
+    X, y = T.make_logreg_data(Nrows, D, seed=5)
+    tgt = T.LogisticRegression(X, y, 0.01)
+    tgt.structured_dmetric = Nrows * D ** 3 > 1e9
+    t64 = T.LogisticRegression(X.astype(np.float64), y.astype(np.float64), 0.01, dtype=np.float64)
+    t64.structured_dmetric = tgt.structured_dmetric
+    rng = np.random.default_rng(D)
+    q = (0.2 * rng.standard_normal((C, D))).astype(np.float32)
+    p = (np.sqrt(Nrows) * 0.3 * rng.standard_normal((C, D))).astype(np.float32)
+    qi = (q + 0.01 * rng.standard_normal((C, D))).astype(np.float32)
+    pi = (p + 0.1 * rng.standard_normal((C, D))).astype(np.float32)
+    he = 0.05
+    dT64, v64 = S._rmhmc_kinetic_grad(t64, q.astype(np.float64), p.astype(np.float64))
+    g64 = t64.grad(q.astype(np.float64))
+    target = g.logistic_regression(_t(X, cuda), _t(y, cuda), 0.01)
+    out = target.midpoint_map(_t(q, cuda), _t(p, cuda), _t(qi, cuda), _t(pi, cuda), he)
+    n = lambda k: out[k].cpu().numpy().astype(np.float64)
+    vs = np.abs(v64).max(axis=1, keepdims=True)
+    assert (np.abs(n("velocity") - v64) / vs).max() < 2e-4
+    gs = np.abs(g64).max(axis=1, keepdims=True)
+    assert (np.abs(n("logdensity_grad") - g64) / gs).max() < 2e-5
+    np.testing.assert_allclose(n("logdensity"), t64.logp(q.astype(np.float64)), rtol=2e-5)
+    np.testing.assert_allclose(n("logdet"), np.linalg.slogdet(t64.metric(q.astype(np.float64)))[1], rtol=1e-5, atol=1e-3)
+    ds = np.abs(dT64).max(axis=1, keepdims=True)
+    assert (np.abs(n("dTdq") - dT64) / ds).max() < 5e-4
+    qn64 = qi.astype(np.float64) + he * v64
+    pn64 = pi.astype(np.float64) - he * (dT64 - g64)
+    assert (np.abs(n("q") - qn64) / np.abs(qn64).max(axis=1, keepdims=True)).max() < 2e-4
+    assert (np.abs(n("p") - pn64) / np.abs(pn64).max(axis=1, keepdims=True)).max() < 2e-4
