@@ -101,6 +101,7 @@ PROTOTYPES = {
     "gb200_logreg_midpoint_map": (C.c_int, [_P(TargetDesc), vp, vp, vp, vp, _dbl, vp, vp, vp, vp, vp, vp, vp, vp, _i64, _i64,
                                             _i32, vp]),
     "gb200_logreg_midpoint_map_workspace": (_i64, [_P(TargetDesc), _i64]),
+    "gb200_logreg_state_eval": (C.c_int, [_P(TargetDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, _i64, _i64, _i32, vp]),
     "gb200_fp32_peak_kernel": (C.c_int, [vp, _i32, _i32, _i64, vp]),
     "gb200_flops_per_chain_step": (_dbl, [_i32, _P(TargetDesc)]),
     "gb200_flops_per_transition": (_dbl, [_i32, _P(TargetDesc)]),

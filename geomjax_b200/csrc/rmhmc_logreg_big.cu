@@ -665,8 +665,10 @@ __global__ void __launch_bounds__(LS_THREADS) ls_grad_kernel(const float* __rest
 }
 
 // CTA per chain: G[c] -> Cholesky -> log-det -> G^-1 (written back in place) and w = G^-1 p
+// z != NULL: momentum draw p = L z (rmhmc/metrics.py:45-58), written to p_out and used for w
 __global__ void __launch_bounds__(BG_THREADS, 1) ls_factor_kernel(float* __restrict__ G, const float* __restrict__ p, int D,
-                                                                  float* __restrict__ w, float* __restrict__ logdet) {
+                                                                  float* __restrict__ w, float* __restrict__ logdet,
+                                                                  const float* __restrict__ z, float* __restrict__ p_out) {
   extern __shared__ __align__(128) unsigned char bg_raw[];
   __shared__ float red[32];
   BigLR tg;
@@ -679,9 +681,20 @@ __global__ void __launch_bounds__(BG_THREADS, 1) ls_factor_kernel(float* __restr
   const int tid = threadIdx.x;
   float* Gc = G + (size_t)c * D * D;
   for (int e = tid; e < D * D; e += BG_THREADS) sm.G[(e / D) * BG_LD + (e % D)] = Gc[e];
-  if (tid < D) sm.v(B_P)[tid] = p[c * D + tid];
+  if (tid < D) sm.v(B_P)[tid] = (z != nullptr) ? z[c * D + tid] : p[c * D + tid];
   __syncthreads();
   const float ld = bg_cholesky(tg, sm, red);
+  if (z != nullptr) {
+    float pv = 0.f;
+    if (tid < D)
+      for (int j = 0; j <= tid; ++j) pv = fmaf(sm.G[tid * BG_LD + j], sm.v(B_P)[j], pv);
+    __syncthreads();
+    if (tid < D) {
+      sm.v(B_P)[tid] = pv;
+      p_out[c * D + tid] = pv;
+    }
+    __syncthreads();
+  }
   bg_inverse(tg, sm);
   bg_matvec(tg, sm, sm.v(B_P), sm.v(B_W));
   for (int e = tid; e < D * D; e += BG_THREADS) Gc[e] = sm.G[(e / D) * BG_LD + (e % D)];
@@ -785,13 +798,54 @@ int gb200_logreg_midpoint_map(const gb200_target_desc* t, const void* q, const v
   ls_grad_kernel<<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, (const float*)t->y, N, D, (float)t->params[0], eta,
                                                        ldn, (const float*)q, (float*)logdensity, (float*)logdensity_grad);
   GB_CHECK_LAUNCH();
-  ls_factor_kernel<<<(unsigned)C, BG_THREADS, sm_f, s>>>(G, (const float*)p, D, (float*)velocity, (float*)logdet);
+  ls_factor_kernel<<<(unsigned)C, BG_THREADS, sm_f, s>>>(G, (const float*)p, D, (float*)velocity, (float*)logdet, nullptr, nullptr);
   GB_CHECK_LAUNCH();
   rc = gb200_logreg_quadform(t, G, h, ldn, gemm_ws, gemm, C, dtype, stream);
   if (rc) return rc;
   ls_finish_kernel<<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, N, D, eta, h, ldn, (const float*)velocity,
                                                          (const float*)logdensity_grad, (const float*)qi, (const float*)pi,
                                                          (float)half_step, (float*)qn, (float*)pn, (float*)dTdq);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+
+// logdensity, gradient, log det G(q) and velocity = G(q)^-1 p for all chains; with z != NULL the momentum is
+// drawn first, p = chol(G(q)) z (rmhmc/metrics.py:45-58), and written to p_out.  The pieces of a transition's
+// start and end (rmhmc/rmhmc.py:158-171) on the same pipeline as gb200_logreg_midpoint_map (no second GEMM).
+int gb200_logreg_state_eval(const gb200_target_desc* t, const void* q, const void* p, const void* z, void* p_out,
+                            void* logdensity, void* logdensity_grad, void* velocity, void* logdet, void* workspace,
+                            int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream) {
+  if (!t || t->kind != GB200_TARGET_LOGREG) { set_error("state_eval: needs a logistic-regression target"); return GB200_ERR_INVALID_ARGUMENT; }
+  if (dtype != GB200_F32) { set_error("state_eval: float32 only"); return GB200_ERR_UNSUPPORTED; }
+  if (C == 0) return GB200_OK;
+  if (!q || (!p && !z) || (z && !p_out) || !logdensity || !logdensity_grad || !velocity || !logdet || !workspace || C < 0 ||
+      !t->vec0 || !t->y) { set_error("state_eval: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
+  const int N = (int)t->N, D = t->D, ldx = (int)t->params[1];
+  if (D > BG_DMAX) { set_error("state_eval: D=%d > %d", D, BG_DMAX); return GB200_ERR_UNSUPPORTED; }
+  if (workspace_bytes < gb200_logreg_midpoint_map_workspace(t, C) || ((uintptr_t)workspace & 255) != 0) {
+    set_error("state_eval: workspace too small or not 256-byte aligned (size: gb200_logreg_midpoint_map_workspace)");
+    return GB200_ERR_INVALID_ARGUMENT;
+  }
+  const int64_t ldn = ((int64_t)N + 3) / 4 * 4;
+  const int64_t fw = gb200_logreg_fisher_metric_workspace(t, C), qw = gb200_logreg_quadform_workspace(t, C);
+  const int64_t gemm = ls_align(fw > qw ? fw : qw);
+  unsigned char* b = (unsigned char*)workspace;
+  unsigned char* gemm_ws = b; b += gemm;
+  float* eta = (float*)b; b += 2 * ls_align(C * ldn * 4);
+  float* G = (float*)b;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = fisher_metric_launch(t, q, G, gemm_ws, gemm, C, dtype, eta, ldn, stream);
+  if (rc) return rc;
+  const size_t sm_n = (size_t)(ldn + 128) * 4;
+  cudaError_t e = cudaFuncSetAttribute(ls_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
+  const size_t sm_f = sizeof(float) * (2 * (size_t)BG_ROWS * BG_LD + BG_NV * 128) + 64;
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
+  if (e != cudaSuccess) { set_error("state_eval: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
+  ls_grad_kernel<<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, (const float*)t->y, N, D, (float)t->params[0], eta,
+                                                       ldn, (const float*)q, (float*)logdensity, (float*)logdensity_grad);
+  GB_CHECK_LAUNCH();
+  ls_factor_kernel<<<(unsigned)C, BG_THREADS, sm_f, s>>>(G, (const float*)p, D, (float*)velocity, (float*)logdet, (const float*)z,
+                                                         (float*)p_out);
   GB_CHECK_LAUNCH();
   return GB200_OK;
 }

@@ -244,6 +244,12 @@ int gb200_logreg_midpoint_map(const gb200_target_desc* target, const void* q, co
                               void* logdet, void* dTdq, void* workspace, int64_t workspace_bytes, int64_t C, int32_t dtype,
                               void* stream);
 int64_t gb200_logreg_midpoint_map_workspace(const gb200_target_desc* target, int64_t C);
+/* Start / end of a transition on the same pipeline (rmhmc/rmhmc.py:158-171): logdensity, gradient, log det G(q) and
+ * velocity = G(q)^-1 p for all chains; with z != NULL the momentum p = chol(G(q)) z is drawn first and written to
+ * p_out (rmhmc/metrics.py:45-58).  Workspace size: gb200_logreg_midpoint_map_workspace. */
+int gb200_logreg_state_eval(const gb200_target_desc* target, const void* q, const void* p, const void* z, void* p_out,
+                            void* logdensity, void* logdensity_grad, void* velocity, void* logdet, void* workspace,
+                            int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Runs a dependent-FMA microbenchmark (iters FFMA per thread on grid x block threads) for the FP32

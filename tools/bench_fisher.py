@@ -36,3 +36,9 @@ for (N, D, C) in ((1000, 25, 16384), (10000, 100, 2048)):
     ms, h = timed(lambda: t.quadratic_forms(A))
     print(f"quadratic_forms  N={N} D={D} C={C}: {ms:.3f} ms per call; algorithmic {2.0 * N * P * C / ms / 1e9:.2f} TFLOP/s "
           f"(x3 TF32 passes = {6.0 * N * P * C / ms / 1e9:.2f} tensor TFLOP/s)")
+    # one lock-step evaluation of the implicit-midpoint map for all chains (both GEMMs + batched Cholesky + O(ND) kernels)
+    p = torch.randn((C, D), device=dev) * (N ** 0.5) * 0.3
+    ms, out = timed(lambda: t.midpoint_map(q, p, q, p, 0.05), reps=5)
+    feval = 2.0 * N * D * D + 10.0 * N * D + D ** 3
+    print(f"midpoint_map     N={N} D={D} C={C}: {ms:.3f} ms per call = {C / ms * 1e3:.0f} chain-evaluations/s; "
+          f"algorithmic {feval * C / ms / 1e9:.2f} TFLOP/s")
