@@ -6,8 +6,9 @@ Semantics are the reference's under ``jax.vmap``: rmhmc/rmhmc.py:131-174 (kernel
 flip), rmhmc/integrators.py:53-89 (``solve_fixed_point_iteration``: a vmapped ``while_loop`` runs until every
 chain is done, converged chains keep their iterate -- masked commits), :92-156 (implicit midpoint),
 mcmc/proposal.py:87-121,168-185 (energy difference, accept).  The host loop below only sequences launches and
-does the O(C D) book-keeping (masks, norms, selects) with torch element-wise ops; everything O(N D) and
-above is in the CUDA library.  One device->host read per fixed-point iteration ("is any chain still active").
+does the O(C D) book-keeping (masks, norms, selects, compaction of the still-active chains) with torch
+element-wise ops; everything O(N D) and above is in the CUDA library.  One device->host read per fixed-point
+iteration (which chains are still active).
 """
 from __future__ import annotations
 
@@ -39,6 +40,7 @@ class _Pipe:
 
     def state_eval(self, q, p=None, z=None):
         D = self.t.D
+        assert q.shape[0] == self.C
         out = dict(logdensity=self._new(self.C), logdensity_grad=self._new(self.C, D), velocity=self._new(self.C, D),
                    logdet=self._new(self.C), momentum=self._new(self.C, D) if z is not None else p)
         with torch.cuda.device(self.dev):
@@ -50,13 +52,14 @@ class _Pipe:
         return out
 
     def midpoint_map(self, q, p, qi, pi, he):
-        D = self.t.D
-        qn, pn = self._new(self.C, D), self._new(self.C, D)
-        lp, g, v, ld = self._new(self.C), self._new(self.C, D), self._new(self.C, D), self._new(self.C)
+        """One evaluation for the ``q.shape[0] <= C`` chains passed in (a compacted sub-batch reuses the workspace)."""
+        D, Ca = self.t.D, q.shape[0]
+        qn, pn = self._new(Ca, D), self._new(Ca, D)
+        lp, g, v, ld = self._new(Ca), self._new(Ca, D), self._new(Ca, D), self._new(Ca)
         with torch.cuda.device(self.dev):
             N.check(N.lib().gb200_logreg_midpoint_map(C.byref(self.desc), N.ptr(q), N.ptr(p), N.ptr(qi), N.ptr(pi), float(he),
                                                       N.ptr(qn), N.ptr(pn), N.ptr(lp), N.ptr(g), N.ptr(v), N.ptr(ld), None,
-                                                      self.wsp, self.ws_bytes, self.C, N.F32, N.stream_ptr()))
+                                                      self.wsp, self.ws_bytes, Ca, N.F32, N.stream_ptr()))
         return qn, pn
 
 
@@ -111,13 +114,23 @@ class rmhmc_lockstep:
                 n = torch.zeros(C_, dtype=torch.int32, device=dev)
                 while True:
                     active = (n < max_iters) & (nrm < inf) & (nrm < divergence_tol) & (nrm > convergence_tol)
-                    if not bool(active.any()):                 # vmapped while_loop: until every chain is done
+                    idx = active.nonzero().squeeze(1)          # vmapped while_loop: until every chain is done
+                    if idx.numel() == 0:
                         break
-                    qc, pc = pipe.midpoint_map(q, p, qi, pi, he)
-                    nc = _norm(qc, pc, q, p)
-                    a = active[:, None]
-                    q, p = torch.where(a, qc, q), torch.where(a, pc, p)
-                    nrm = torch.where(active, nc, nrm)
+                    # The fixed-point count is heavy-tailed (a float32 iterate stalling just above tol runs to
+                    # max_iters): evaluate the map only for the chains that are still iterating.  Chains are
+                    # independent, so compaction changes no chain's numbers -- only how many ride along.
+                    full = idx.numel() == C_
+                    qa, pa = (q, p) if full else (q[idx], p[idx])
+                    qia, pia = (qi, pi) if full else (qi[idx], pi[idx])
+                    qc, pc = pipe.midpoint_map(qa.contiguous(), pa.contiguous(), qia.contiguous(), pia.contiguous(), he)
+                    nc = _norm(qc, pc, qa, pa)
+                    if full:
+                        q, p, nrm = qc, pc, nc
+                    else:
+                        q = q.index_copy(0, idx, qc)
+                        p = p.index_copy(0, idx, pc)
+                        nrm = nrm.index_copy(0, idx, nc)
                     n = n + active.to(torch.int32)
                 iters += n
                 q, p = pipe.midpoint_map(q, p, q, p, he)       # explicit update from the midpoint :147-148
