@@ -8,7 +8,8 @@ import torch
 import geomjax_b200 as g
 from oracle.targets import make_logreg_data
 
-N, D, L, eps = 10000, 100, 6, 0.05
+N, D, L = int(os.environ.get("ROWS", 10000)), int(os.environ.get("DIM", 100)), 6
+eps = float(os.environ.get("EPS", 0.05))
 C = int(os.environ.get("CHAINS", 2048))
 X, y = make_logreg_data(N, D, 0)
 dev = torch.device("cuda:0")
