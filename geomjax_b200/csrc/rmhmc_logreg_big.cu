@@ -621,55 +621,29 @@ int launch_init_logreg_big(const gb200_target_desc& t, gb200_state st, long long
 // =====================================================================================================
 // Lock-step evaluation of the implicit-midpoint map for ALL chains at once (rmhmc/integrators.py:119-142)
 // with both D^2 N products on the warp-specialised tcgen05 GEMMs of fisher_tc.cu:
-//   pre-kernel (eta, W tiles) -> GEMM vec(G) = Z^T W -> ls_resid_kernel (logp, r = y - s) -> ls_xtt_kernel<0> (grad = X^T r)
+//   pre-kernel (eta, W tiles) -> GEMM vec(G) = Z^T W -> [ls_grad_kernel: logp, gradient]
 //   -> ls_factor_kernel (CTA per chain: Cholesky, log-det, G^-1 in place, w = G^-1 p)
-//   -> GEMM h = Z vecsym(G^-1) -> ls_xv_kernel (u = X w, t = w'(h - u^2)) -> ls_xtt_kernel<1> (dT = 1/2 X^T t, candidate).
-// The O(N D) kernels are tiled over CHAINS (64 / 32 per CTA) so that the 4 MB design matrix is read once per tile:
-// a first version ran one CTA per chain and moved 24 GB through L2 per evaluation at c5's shape.
+//   -> GEMM h = Z vecsym(G^-1) -> ls_finish_kernel (u = X w, t = w'(h - u^2), dT = 1/2 X^T t, candidate iterate).
 // This is ONE evaluation of the map (the unit the fixed-point loop repeats); the sampler loop around it
 // (masked commits, accept) is the next step.
 // =====================================================================================================
 constexpr int LS_THREADS = 256;
 
-// ---- chain-tiled O(N D) kernels: the design matrix is read once per TILE of chains, not once per chain ----------
-constexpr int LX_TN = 128;   // data rows per tile
-constexpr int LX_LD = 132;   // row stride of the staged X tile (16-byte aligned rows, conflict-free float4 reads)
-
-__device__ __forceinline__ void lx_load_x(const float* __restrict__ Xt, int ldx, int N, int D, int n0, float* Xs) {
-  for (int e = threadIdx.x; e < D * (LX_TN / 4); e += blockDim.x) {
-    const int i = e >> 5, c4 = e & 31;
-    const int n = n0 + 4 * c4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n < ldx) {
-      v = __ldg((const float4*)(Xt + (size_t)i * ldx + n));
-      if (n + 0 >= N) v.x = 0.f;
-      if (n + 1 >= N) v.y = 0.f;
-      if (n + 2 >= N) v.z = 0.f;
-      if (n + 3 >= N) v.w = 0.f;
-    }
-    *(float4*)(Xs + i * LX_LD + 4 * c4) = v;
-  }
-}
-
-// r[c, n] = y_n - sigmoid(eta[c, n]) and logp[c]  (CTA per chain; reads eta only)
-__global__ void __launch_bounds__(LS_THREADS) ls_resid_kernel(const float* __restrict__ y, int N, int D, float alpha,
-                                                              const float* __restrict__ eta, long long ld_eta,
-                                                              const float* __restrict__ q, float* __restrict__ r,
-                                                              float* __restrict__ logp) {
+// logp[c] and grad[c, :] from eta[c, :]  (CTA per chain)
+__global__ void __launch_bounds__(LS_THREADS) ls_grad_kernel(const float* __restrict__ Xt, int ldx, const float* __restrict__ y,
+                                                             int N, int D, float alpha, const float* __restrict__ eta,
+                                                             long long ld_eta, const float* __restrict__ q,
+                                                             float* __restrict__ logp, float* __restrict__ grad) {
+  extern __shared__ float ls_sm[];  // r[N4]
   __shared__ float red[32];
   const long long c = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* e = eta + c * ld_eta;
-  float* rc = r + c * ld_eta;
   float lp = 0.f;
-  for (int n = tid; n < ld_eta; n += LS_THREADS) {
-    float rv = 0.f;
-    if (n < N) {
-      const float et = e[n], yn = y[n];
-      lp += yn * et - (fmaxf(et, 0.f) + log1pf(expf(-fabsf(et))));
-      rv = yn - 1.f / (1.f + expf(-et));
-    }
-    rc[n] = rv;
+  for (int n = tid; n < N; n += LS_THREADS) {
+    const float et = e[n], yn = y[n];
+    lp += yn * et - (fmaxf(et, 0.f) + log1pf(expf(-fabsf(et))));
+    ls_sm[n] = yn - 1.f / (1.f + expf(-et));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
@@ -681,114 +655,12 @@ __global__ void __launch_bounds__(LS_THREADS) ls_resid_kernel(const float* __res
     for (int i = 0; i < D; ++i) qq = fmaf(q[c * D + i], q[c * D + i], qq);
     logp[c] = t - 0.5f * alpha * qq;
   }
-}
-
-// t[c, n] = w'(eta[c, n]) (h[c, n] - u^2),  u = x_n . w_c, written over h.  CTA = 128 data rows x 64 chains.
-__global__ void __launch_bounds__(256) ls_xv_kernel(const float* __restrict__ Xt, int ldx, int N, int D,
-                                                    const float* __restrict__ w, long long C,
-                                                    const float* __restrict__ eta, float* __restrict__ h, long long ld_eta) {
-  extern __shared__ __align__(16) float lx_sm[];
-  float* Xs = lx_sm;                 // [D][LX_LD]
-  float* wT = lx_sm + D * LX_LD;     // [D][64]: w of the 64 chains, chain-minor
-  const int n0 = blockIdx.x * LX_TN;
-  const long long c0 = (long long)blockIdx.y * 64;
-  const int tid = threadIdx.x;
-  lx_load_x(Xt, ldx, N, D, n0, Xs);
-  for (int e = tid; e < D * 64; e += 256) {
-    const int cc = e / D, i = e - cc * D;
-    wT[i * 64 + cc] = (c0 + cc < C) ? w[(c0 + cc) * D + i] : 0.f;
-  }
-  __syncthreads();
-  const int n = tid & 127, cg = tid >> 7;  // 2 groups of 32 chains
-  float acc[32];
+  for (int i = warp; i < D; i += LS_THREADS / 32) {
+    float a = 0.f;
+    for (int n = lane; n < N; n += 32) a = fmaf(Xt[(size_t)i * ldx + n], ls_sm[n], a);
 #pragma unroll
-  for (int k = 0; k < 32; ++k) acc[k] = 0.f;
-  for (int i = 0; i < D; ++i) {
-    const float x = Xs[i * LX_LD + n];
-    const float4* w4 = (const float4*)(wT + i * 64 + cg * 32);
-#pragma unroll
-    for (int k4 = 0; k4 < 8; ++k4) {
-      const float4 v = w4[k4];
-      acc[4 * k4 + 0] = fmaf(x, v.x, acc[4 * k4 + 0]);
-      acc[4 * k4 + 1] = fmaf(x, v.y, acc[4 * k4 + 1]);
-      acc[4 * k4 + 2] = fmaf(x, v.z, acc[4 * k4 + 2]);
-      acc[4 * k4 + 3] = fmaf(x, v.w, acc[4 * k4 + 3]);
-    }
-  }
-  if (n0 + n < N) {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const long long c = c0 + cg * 32 + k;
-      if (c < C) {
-        const long long o = c * ld_eta + n0 + n;
-        const float s = 1.f / (1.f + expf(-eta[o]));
-        const float u = acc[k];
-        h[o] = s * (1.f - s) * (1.f - 2.f * s) * (h[o] - u * u);
-      }
-    }
-  }
-}
-
-// out[c, i] = scale * sum_n X[n, i] t[c, n]  (+ epilogue).  CTA = 32 chains, loops over all data-row tiles.
-//   MODE 0: grad[c, i] = sum - alpha q[c, i]
-//   MODE 1: dT = sum / 2;  qn = qi + he w,  pn = pi - he (dT - grad)
-template <int MODE>
-__global__ void __launch_bounds__(256) ls_xtt_kernel(const float* __restrict__ Xt, int ldx, int N, int D,
-                                                     const float* __restrict__ t, long long ld_t, long long C, float alpha,
-                                                     const float* __restrict__ q, float* __restrict__ grad,
-                                                     const float* __restrict__ w, const float* __restrict__ qi,
-                                                     const float* __restrict__ pi, float he, float* __restrict__ qn,
-                                                     float* __restrict__ pn, float* __restrict__ dT_out) {
-  extern __shared__ __align__(16) float lx_sm[];
-  float* Xs = lx_sm;                 // [D][LX_LD]
-  float* ts = lx_sm + D * LX_LD;     // [32][LX_LD]
-  const long long c0 = (long long)blockIdx.x * 32;
-  const int tid = threadIdx.x;
-  const int i = tid & 127, cg = tid >> 7;  // feature, group of 16 chains
-  const bool live = i < D;
-  float acc[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-  for (int n0 = 0; n0 < N; n0 += LX_TN) {
-    __syncthreads();
-    lx_load_x(Xt, ldx, N, D, n0, Xs);
-    for (int e = tid; e < 32 * (LX_TN / 4); e += 256) {
-      const int cc = e >> 5, c4 = e & 31;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c0 + cc < C && n0 + 4 * c4 < ld_t) v = *(const float4*)(t + (c0 + cc) * ld_t + n0 + 4 * c4);  // rows >= N hold zeros
-      *(float4*)(ts + cc * LX_LD + 4 * c4) = v;
-    }
-    __syncthreads();
-    if (live) {
-      const float* xr = Xs + i * LX_LD;
-      const float* tr = ts + cg * 16 * LX_LD;
-#pragma unroll 2
-      for (int c4 = 0; c4 < LX_TN / 4; ++c4) {
-        const float4 x = *(const float4*)(xr + 4 * c4);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float4 v = *(const float4*)(tr + k * LX_LD + 4 * c4);
-          acc[k] = fmaf(x.x, v.x, fmaf(x.y, v.y, fmaf(x.z, v.z, fmaf(x.w, v.w, acc[k]))));
-        }
-      }
-    }
-  }
-  if (live) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const long long c = c0 + cg * 16 + k;
-      if (c < C) {
-        const long long o = c * D + i;
-        if (MODE == 0) {
-          grad[o] = acc[k] - alpha * q[o];
-        } else {
-          const float dT = 0.5f * acc[k];
-          if (dT_out) dT_out[o] = dT;
-          qn[o] = fmaf(he, w[o], qi[o]);
-          pn[o] = fmaf(-he, dT - grad[o], pi[o]);
-        }
-      }
-    }
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) grad[c * D + i] = a - alpha * q[c * D + i];
   }
 }
 
@@ -828,6 +700,44 @@ __global__ void __launch_bounds__(BG_THREADS, 1) ls_factor_kernel(float* __restr
   for (int e = tid; e < D * D; e += BG_THREADS) Gc[e] = sm.G[(e / D) * BG_LD + (e % D)];
   if (tid < D) w[c * D + tid] = sm.v(B_W)[tid];
   if (tid == 0) logdet[c] = ld;
+}
+
+// CTA per chain: dT/dq and the candidate iterate (qn, pn) = (qi + he w, pi - he (dT - grad))
+__global__ void __launch_bounds__(LS_THREADS) ls_finish_kernel(const float* __restrict__ Xt, int ldx, int N, int D,
+                                                               const float* __restrict__ eta, const float* __restrict__ h,
+                                                               long long ld_eta, const float* __restrict__ w,
+                                                               const float* __restrict__ grad, const float* __restrict__ qi,
+                                                               const float* __restrict__ pi, float he,
+                                                               float* __restrict__ qn, float* __restrict__ pn,
+                                                               float* __restrict__ dT_out) {
+  extern __shared__ float ls_sm[];  // t[N4] then w[D]
+  const long long c = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* ws = ls_sm + (N + 3) / 4 * 4;
+  if (tid < D) ws[tid] = w[c * D + tid];
+  __syncthreads();
+  const float* e = eta + c * ld_eta;
+  const float* hc = h + c * ld_eta;
+  for (int n = tid; n < N; n += LS_THREADS) {
+    float u = 0.f;
+    for (int i = 0; i < D; ++i) u = fmaf(Xt[(size_t)i * ldx + n], ws[i], u);
+    const float s = 1.f / (1.f + expf(-e[n]));
+    ls_sm[n] = s * (1.f - s) * (1.f - 2.f * s) * (hc[n] - u * u);
+  }
+  __syncthreads();
+  for (int i = warp; i < D; i += LS_THREADS / 32) {
+    float a = 0.f;
+    for (int n = lane; n < N; n += 32) a = fmaf(Xt[(size_t)i * ldx + n], ls_sm[n], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      const float dT = 0.5f * a;
+      const long long k = c * D + i;
+      if (dT_out) dT_out[k] = dT;
+      qn[k] = fmaf(he, ws[i], qi[k]);
+      pn[k] = fmaf(-he, dT - grad[k], pi[k]);
+    }
+  }
 }
 
 int fisher_metric_launch(const gb200_target_desc* t, const void* position, void* metric, void* workspace,
@@ -879,33 +789,22 @@ int gb200_logreg_midpoint_map(const gb200_target_desc* t, const void* q, const v
   cudaStream_t s = (cudaStream_t)stream;
   int rc = fisher_metric_launch(t, q, G, gemm_ws, gemm, C, dtype, eta, ldn, stream);
   if (rc) return rc;
-  const size_t sm_x = sizeof(float) * ((size_t)D * LX_LD + (size_t)(32 * LX_LD > D * 64 ? 32 * LX_LD : D * 64)) + 64;
-  float* hbuf = h;
-  cudaError_t e = cudaFuncSetAttribute(ls_xtt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_xtt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_xv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x);
+  const size_t sm_n = (size_t)(ldn + 128) * 4;
+  cudaError_t e = cudaFuncSetAttribute(ls_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
   const size_t sm_f = sizeof(float) * (2 * (size_t)BG_ROWS * BG_LD + BG_NV * 128) + 64;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
   if (e != cudaSuccess) { set_error("midpoint_map: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
-  // residuals r = y - s into the (still unused) h buffer + logp, then grad = X^T r - alpha q per tile of 32 chains
-  ls_resid_kernel<<<(unsigned)C, LS_THREADS, 0, s>>>((const float*)t->y, N, D, (float)t->params[0], eta, ldn, (const float*)q, hbuf,
-                                                     (float*)logdensity);
-  GB_CHECK_LAUNCH();
-  ls_xtt_kernel<0><<<(unsigned)((C + 31) / 32), 256, sm_x, s>>>((const float*)t->vec0, ldx, N, D, hbuf, ldn, C, (float)t->params[0],
-                                                              (const float*)q, (float*)logdensity_grad, nullptr, nullptr, nullptr,
-                                                              0.f, nullptr, nullptr, nullptr);
+  ls_grad_kernel<<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, (const float*)t->y, N, D, (float)t->params[0], eta,
+                                                       ldn, (const float*)q, (float*)logdensity, (float*)logdensity_grad);
   GB_CHECK_LAUNCH();
   ls_factor_kernel<<<(unsigned)C, BG_THREADS, sm_f, s>>>(G, (const float*)p, D, (float*)velocity, (float*)logdet, nullptr, nullptr);
   GB_CHECK_LAUNCH();
   rc = gb200_logreg_quadform(t, G, h, ldn, gemm_ws, gemm, C, dtype, stream);
   if (rc) return rc;
-  ls_xv_kernel<<<dim3((unsigned)((N + LX_TN - 1) / LX_TN), (unsigned)((C + 63) / 64)), 256, sm_x, s>>>(
-      (const float*)t->vec0, ldx, N, D, (const float*)velocity, C, eta, h, ldn);
-  GB_CHECK_LAUNCH();
-  ls_xtt_kernel<1><<<(unsigned)((C + 31) / 32), 256, sm_x, s>>>((const float*)t->vec0, ldx, N, D, h, ldn, C, 0.f, nullptr,
-                                                              (float*)logdensity_grad, (const float*)velocity, (const float*)qi,
-                                                              (const float*)pi, (float)half_step, (float*)qn, (float*)pn,
-                                                              (float*)dTdq);
+  ls_finish_kernel<<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, N, D, eta, h, ldn, (const float*)velocity,
+                                                         (const float*)logdensity_grad, (const float*)qi, (const float*)pi,
+                                                         (float)half_step, (float*)qn, (float*)pn, (float*)dTdq);
   GB_CHECK_LAUNCH();
   return GB200_OK;
 }
@@ -937,19 +836,13 @@ int gb200_logreg_state_eval(const gb200_target_desc* t, const void* q, const voi
   cudaStream_t s = (cudaStream_t)stream;
   int rc = fisher_metric_launch(t, q, G, gemm_ws, gemm, C, dtype, eta, ldn, stream);
   if (rc) return rc;
-  const size_t sm_x = sizeof(float) * ((size_t)D * LX_LD + (size_t)(32 * LX_LD > D * 64 ? 32 * LX_LD : D * 64)) + 64;
-  float* hbuf = eta + ls_align(C * ldn * 4) / 4;
-  cudaError_t e = cudaFuncSetAttribute(ls_xtt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x);
+  const size_t sm_n = (size_t)(ldn + 128) * 4;
+  cudaError_t e = cudaFuncSetAttribute(ls_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
   const size_t sm_f = sizeof(float) * (2 * (size_t)BG_ROWS * BG_LD + BG_NV * 128) + 64;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
   if (e != cudaSuccess) { set_error("state_eval: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
-  // residuals r = y - s into the (still unused) h buffer + logp, then grad = X^T r - alpha q per tile of 32 chains
-  ls_resid_kernel<<<(unsigned)C, LS_THREADS, 0, s>>>((const float*)t->y, N, D, (float)t->params[0], eta, ldn, (const float*)q, hbuf,
-                                                     (float*)logdensity);
-  GB_CHECK_LAUNCH();
-  ls_xtt_kernel<0><<<(unsigned)((C + 31) / 32), 256, sm_x, s>>>((const float*)t->vec0, ldx, N, D, hbuf, ldn, C, (float)t->params[0],
-                                                              (const float*)q, (float*)logdensity_grad, nullptr, nullptr, nullptr,
-                                                              0.f, nullptr, nullptr, nullptr);
+  ls_grad_kernel<<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, (const float*)t->y, N, D, (float)t->params[0], eta,
+                                                       ldn, (const float*)q, (float*)logdensity, (float*)logdensity_grad);
   GB_CHECK_LAUNCH();
   ls_factor_kernel<<<(unsigned)C, BG_THREADS, sm_f, s>>>(G, (const float*)p, D, (float*)velocity, (float*)logdet, (const float*)z,
                                                          (float*)p_out);
