@@ -632,66 +632,38 @@ int launch_init_logreg_big(const gb200_target_desc& t, gb200_state st, long long
 // =====================================================================================================
 constexpr int LS_THREADS = 256;
 
-// logp[c] and grad[c, :] from eta[c, :].  CPC chains per CTA share every load of the design matrix (L2 -> SM traffic
-// is what bounds these kernels: 4 MB of X per chain at c5's shape); CPC = 1 keeps one CTA per chain for small
-// (compacted) batches, where filling the SMs matters more.
-template <int CPC>
+// logp[c] and grad[c, :] from eta[c, :]  (CTA per chain)
 __global__ void __launch_bounds__(LS_THREADS) ls_grad_kernel(const float* __restrict__ Xt, int ldx, const float* __restrict__ y,
                                                              int N, int D, float alpha, const float* __restrict__ eta,
-                                                             long long ld_eta, const float* __restrict__ q, long long C,
+                                                             long long ld_eta, const float* __restrict__ q,
                                                              float* __restrict__ logp, float* __restrict__ grad) {
-  extern __shared__ float ls_sm[];  // r[CPC][N4]
-  __shared__ float red[CPC][LS_THREADS / 32];
-  const long long c0 = (long long)blockIdx.x * CPC;
+  extern __shared__ float ls_sm[];  // r[N4]
+  __shared__ float red[32];
+  const long long c = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N4 = (N + 3) / 4 * 4;
-  float lp[CPC];
-#pragma unroll
-  for (int k = 0; k < CPC; ++k) lp[k] = 0.f;
+  const float* e = eta + c * ld_eta;
+  float lp = 0.f;
   for (int n = tid; n < N; n += LS_THREADS) {
-    const float yn = y[n];
-#pragma unroll
-    for (int k = 0; k < CPC; ++k) {
-      float rv = 0.f;
-      if (c0 + k < C) {
-        const float et = eta[(c0 + k) * ld_eta + n];
-        lp[k] += yn * et - (fmaxf(et, 0.f) + log1pf(expf(-fabsf(et))));
-        rv = yn - 1.f / (1.f + expf(-et));
-      }
-      ls_sm[k * N4 + n] = rv;
-    }
+    const float et = e[n], yn = y[n];
+    lp += yn * et - (fmaxf(et, 0.f) + log1pf(expf(-fabsf(et))));
+    ls_sm[n] = yn - 1.f / (1.f + expf(-et));
   }
 #pragma unroll
-  for (int k = 0; k < CPC; ++k) {
-    float v = lp[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[k][warp] = v;
-  }
+  for (int o = 16; o > 0; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
+  if (lane == 0) red[warp] = lp;
   __syncthreads();
-  if (tid < CPC && c0 + tid < C) {
-    const long long c = c0 + tid;
+  if (tid == 0) {
     float t = 0.f, qq = 0.f;
-    for (int w = 0; w < LS_THREADS / 32; ++w) t += red[tid][w];
+    for (int w = 0; w < LS_THREADS / 32; ++w) t += red[w];
     for (int i = 0; i < D; ++i) qq = fmaf(q[c * D + i], q[c * D + i], qq);
     logp[c] = t - 0.5f * alpha * qq;
   }
   for (int i = warp; i < D; i += LS_THREADS / 32) {
-    float a[CPC];
+    float a = 0.f;
+    for (int n = lane; n < N; n += 32) a = fmaf(Xt[(size_t)i * ldx + n], ls_sm[n], a);
 #pragma unroll
-    for (int k = 0; k < CPC; ++k) a[k] = 0.f;
-    for (int n = lane; n < N; n += 32) {
-      const float x = Xt[(size_t)i * ldx + n];
-#pragma unroll
-      for (int k = 0; k < CPC; ++k) a[k] = fmaf(x, ls_sm[k * N4 + n], a[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < CPC; ++k) {
-      float v = a[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && c0 + k < C) grad[(c0 + k) * D + i] = v - alpha * q[(c0 + k) * D + i];
-    }
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) grad[c * D + i] = a - alpha * q[c * D + i];
   }
 }
 
@@ -733,67 +705,40 @@ __global__ void __launch_bounds__(BG_THREADS, 1) ls_factor_kernel(float* __restr
   if (tid == 0) logdet[c] = ld;
 }
 
-// dT/dq and the candidate iterate (qn, pn) = (qi + he w, pi - he (dT - grad)); CPC chains per CTA (see ls_grad_kernel)
-template <int CPC>
+// CTA per chain: dT/dq and the candidate iterate (qn, pn) = (qi + he w, pi - he (dT - grad))
 __global__ void __launch_bounds__(LS_THREADS) ls_finish_kernel(const float* __restrict__ Xt, int ldx, int N, int D,
                                                                const float* __restrict__ eta, const float* __restrict__ h,
                                                                long long ld_eta, const float* __restrict__ w,
                                                                const float* __restrict__ grad, const float* __restrict__ qi,
-                                                               const float* __restrict__ pi, float he, long long C,
+                                                               const float* __restrict__ pi, float he,
                                                                float* __restrict__ qn, float* __restrict__ pn,
                                                                float* __restrict__ dT_out) {
-  extern __shared__ float ls_sm[];  // t[CPC][N4] then w[CPC][128]
-  const long long c0 = (long long)blockIdx.x * CPC;
+  extern __shared__ float ls_sm[];  // t[N4] then w[D]
+  const long long c = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N4 = (N + 3) / 4 * 4;
-  float* ws = ls_sm + CPC * N4;
-  for (int e = tid; e < CPC * D; e += LS_THREADS) {
-    const int k = e / D, i = e - k * D;
-    ws[k * 128 + i] = (c0 + k < C) ? w[(c0 + k) * D + i] : 0.f;
-  }
+  float* ws = ls_sm + (N + 3) / 4 * 4;
+  if (tid < D) ws[tid] = w[c * D + tid];
   __syncthreads();
+  const float* e = eta + c * ld_eta;
+  const float* hc = h + c * ld_eta;
   for (int n = tid; n < N; n += LS_THREADS) {
-    float u[CPC];
-#pragma unroll
-    for (int k = 0; k < CPC; ++k) u[k] = 0.f;
-    for (int i = 0; i < D; ++i) {
-      const float x = Xt[(size_t)i * ldx + n];
-#pragma unroll
-      for (int k = 0; k < CPC; ++k) u[k] = fmaf(x, ws[k * 128 + i], u[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < CPC; ++k) {
-      float tv = 0.f;
-      if (c0 + k < C) {
-        const long long o = (c0 + k) * ld_eta + n;
-        const float sg = 1.f / (1.f + expf(-eta[o]));
-        tv = sg * (1.f - sg) * (1.f - 2.f * sg) * (h[o] - u[k] * u[k]);
-      }
-      ls_sm[k * N4 + n] = tv;
-    }
+    float u = 0.f;
+    for (int i = 0; i < D; ++i) u = fmaf(Xt[(size_t)i * ldx + n], ws[i], u);
+    const float s = 1.f / (1.f + expf(-e[n]));
+    ls_sm[n] = s * (1.f - s) * (1.f - 2.f * s) * (hc[n] - u * u);
   }
   __syncthreads();
   for (int i = warp; i < D; i += LS_THREADS / 32) {
-    float a[CPC];
+    float a = 0.f;
+    for (int n = lane; n < N; n += 32) a = fmaf(Xt[(size_t)i * ldx + n], ls_sm[n], a);
 #pragma unroll
-    for (int k = 0; k < CPC; ++k) a[k] = 0.f;
-    for (int n = lane; n < N; n += 32) {
-      const float x = Xt[(size_t)i * ldx + n];
-#pragma unroll
-      for (int k = 0; k < CPC; ++k) a[k] = fmaf(x, ls_sm[k * N4 + n], a[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < CPC; ++k) {
-      float v = a[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && c0 + k < C) {
-        const float dT = 0.5f * v;
-        const long long o = (c0 + k) * D + i;
-        if (dT_out) dT_out[o] = dT;
-        qn[o] = fmaf(he, ws[k * 128 + i], qi[o]);
-        pn[o] = fmaf(-he, dT - grad[o], pi[o]);
-      }
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      const float dT = 0.5f * a;
+      const long long k = c * D + i;
+      if (dT_out) dT_out[k] = dT;
+      qn[k] = fmaf(he, ws[i], qi[k]);
+      pn[k] = fmaf(-he, dT - grad[k], pi[k]);
     }
   }
 }
@@ -847,35 +792,22 @@ int gb200_logreg_midpoint_map(const gb200_target_desc* t, const void* q, const v
   cudaStream_t s = (cudaStream_t)stream;
   int rc = fisher_metric_launch(t, q, G, gemm_ws, gemm, C, dtype, eta, ldn, stream);
   if (rc) return rc;
-  // 4 chains per CTA share the X loads when the batch is large enough to still fill the SMs
-  const int cpc = (C >= 1024 && (size_t)(4 * ldn + 4 * 128) * 4 <= 200 * 1024) ? 4 : 1;
-  const size_t sm_n = (size_t)(cpc * ldn + cpc * 128) * 4;
-  cudaError_t e = cudaFuncSetAttribute(ls_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_grad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_finish_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_finish_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
+  const size_t sm_n = (size_t)(ldn + 128) * 4;
+  cudaError_t e = cudaFuncSetAttribute(ls_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
   const size_t sm_f = sizeof(float) * (2 * (size_t)BG_ROWS * BG_LD + BG_NV * 128) + 64;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
   if (e != cudaSuccess) { set_error("midpoint_map: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
-  if (cpc == 4)
-    ls_grad_kernel<4><<<(unsigned)((C + 3) / 4), LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, (const float*)t->y, N, D, (float)t->params[0],
-                                                                        eta, ldn, (const float*)q, C, (float*)logdensity, (float*)logdensity_grad);
-  else
-    ls_grad_kernel<1><<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, (const float*)t->y, N, D, (float)t->params[0], eta,
-                                                            ldn, (const float*)q, C, (float*)logdensity, (float*)logdensity_grad);
+  ls_grad_kernel<<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, (const float*)t->y, N, D, (float)t->params[0], eta,
+                                                       ldn, (const float*)q, (float*)logdensity, (float*)logdensity_grad);
   GB_CHECK_LAUNCH();
   ls_factor_kernel<<<(unsigned)C, BG_THREADS, sm_f, s>>>(G, (const float*)p, D, (float*)velocity, (float*)logdet, nullptr, nullptr);
   GB_CHECK_LAUNCH();
   rc = gb200_logreg_quadform(t, G, h, ldn, gemm_ws, gemm, C, dtype, stream);
   if (rc) return rc;
-  if (cpc == 4)
-    ls_finish_kernel<4><<<(unsigned)((C + 3) / 4), LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, N, D, eta, h, ldn, (const float*)velocity,
-                                                                          (const float*)logdensity_grad, (const float*)qi, (const float*)pi,
-                                                                          (float)half_step, C, (float*)qn, (float*)pn, (float*)dTdq);
-  else
-    ls_finish_kernel<1><<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, N, D, eta, h, ldn, (const float*)velocity,
-                                                              (const float*)logdensity_grad, (const float*)qi, (const float*)pi,
-                                                              (float)half_step, C, (float*)qn, (float*)pn, (float*)dTdq);
+  ls_finish_kernel<<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, N, D, eta, h, ldn, (const float*)velocity,
+                                                         (const float*)logdensity_grad, (const float*)qi, (const float*)pi,
+                                                         (float)half_step, (float*)qn, (float*)pn, (float*)dTdq);
   GB_CHECK_LAUNCH();
   return GB200_OK;
 }
@@ -907,19 +839,13 @@ int gb200_logreg_state_eval(const gb200_target_desc* t, const void* q, const voi
   cudaStream_t s = (cudaStream_t)stream;
   int rc = fisher_metric_launch(t, q, G, gemm_ws, gemm, C, dtype, eta, ldn, stream);
   if (rc) return rc;
-  const int cpc = (C >= 1024 && (size_t)(4 * ldn + 4 * 128) * 4 <= 200 * 1024) ? 4 : 1;
-  const size_t sm_n = (size_t)(cpc * ldn + cpc * 128) * 4;
-  cudaError_t e = cudaFuncSetAttribute(ls_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_grad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
+  const size_t sm_n = (size_t)(ldn + 128) * 4;
+  cudaError_t e = cudaFuncSetAttribute(ls_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
   const size_t sm_f = sizeof(float) * (2 * (size_t)BG_ROWS * BG_LD + BG_NV * 128) + 64;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
   if (e != cudaSuccess) { set_error("state_eval: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
-  if (cpc == 4)
-    ls_grad_kernel<4><<<(unsigned)((C + 3) / 4), LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, (const float*)t->y, N, D, (float)t->params[0],
-                                                                        eta, ldn, (const float*)q, C, (float*)logdensity, (float*)logdensity_grad);
-  else
-    ls_grad_kernel<1><<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, (const float*)t->y, N, D, (float)t->params[0], eta,
-                                                            ldn, (const float*)q, C, (float*)logdensity, (float*)logdensity_grad);
+  ls_grad_kernel<<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, (const float*)t->y, N, D, (float)t->params[0], eta,
+                                                       ldn, (const float*)q, (float*)logdensity, (float*)logdensity_grad);
   GB_CHECK_LAUNCH();
   ls_factor_kernel<<<(unsigned)C, BG_THREADS, sm_f, s>>>(G, (const float*)p, D, (float*)velocity, (float*)logdet, (const float*)z,
                                                          (float*)p_out);
