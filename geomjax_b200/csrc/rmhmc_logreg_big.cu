@@ -626,7 +626,9 @@ int launch_init_logreg_big(const gb200_target_desc& t, gb200_state st, long long
 //   -> GEMM h = Z vecsym(G^-1) -> ls_finish_kernel (u = X w, t = w'(h - u^2), dT = 1/2 X^T t, candidate iterate).
 // The O(N D) kernels run one CTA per chain.  A chain-tiled variant (X staged once per 32-64 chains, 64 CTAs looping over
 // all data tiles) was measured and reverted: 7.3 vs 6.8 ms per evaluation at c5's shape and 2.0 vs 1.24 s per transition
-// once the active set is compacted to a few chains (X is L2-resident; the per-chain CTAs fill the machine).
+// once the active set is compacted to a few chains (X is L2-resident; the per-chain CTAs fill the machine).  Sharing the
+// X loads between 4 chains per CTA (160 KB of shared memory, one CTA per SM) was slower as well (8.7 ms): these kernels are
+// occupancy / latency bound (5 CTAs of 41 KB per SM), not L2-bandwidth bound.
 // This is ONE evaluation of the map (the unit the fixed-point loop repeats); the sampler loop around it
 // (masked commits, accept) is the next step.
 // =====================================================================================================
