@@ -130,3 +130,13 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and line["gpu_launches"] == 0
+
+
+def test_lockstep_facade_rejects_other_targets():
+    """rmhmc_lockstep is built for the logistic-regression target; anything else is refused up front."""
+    import geomjax_b200 as g
+    t = g.neal_funnel(4)
+    with pytest.raises(NotImplementedError):
+        g.rmhmc_lockstep(t, 0.1, t, 4)
+    with pytest.raises(NotImplementedError):
+        g.rmhmc_lockstep(lambda x: 0.0, 0.1, None, 4)
