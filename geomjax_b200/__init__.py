@@ -10,7 +10,7 @@ from .adaptation import dual_averaging, step_size_adaptation, window_adaptation 
 from .base import AdaptationAlgorithm, AdaptationResults, SamplingAlgorithm  # noqa: F401
 from .samplers import (LMCInfo, LMCState, Proposal, RMHMCInfo, RMHMCState, lmc, lmcmonge, rmhmc,  # noqa: F401
                        run_fused)
-from .lockstep import rmhmc_lockstep  # noqa: F401
+from .plan import LockstepPlan  # noqa: F401
 from .diagnostics import effective_sample_size as ess  # noqa: F401
 from .diagnostics import potential_scale_reduction as rhat  # noqa: F401
 from .targets import TargetDescriptor, banana, gaussian, logistic_regression, neal_funnel, softabs  # noqa: F401

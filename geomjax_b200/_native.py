@@ -64,7 +64,7 @@ class RunOpts(C.Structure):
     _fields_ = [("samples", vp), ("sample_accept", vp), ("noise_override", vp), ("uniform_override", vp),
                 ("dual_averaging", vp), ("da_target", C.c_double), ("da_t0", C.c_double),
                 ("da_gamma", C.c_double), ("da_kappa", C.c_double),
-                ("workspace", vp), ("workspace_bytes", C.c_int64)]
+                ("workspace", vp), ("workspace_bytes", C.c_int64), ("plan", vp)]
 
 
 _i32, _i64, _dbl = C.c_int32, C.c_int64, C.c_double
@@ -98,10 +98,12 @@ PROTOTYPES = {
     "gb200_logreg_fisher_metric_workspace": (_i64, [_P(TargetDesc), _i64]),
     "gb200_logreg_quadform": (C.c_int, [_P(TargetDesc), vp, vp, _i64, vp, _i64, _i64, _i32, vp]),
     "gb200_logreg_quadform_workspace": (_i64, [_P(TargetDesc), _i64]),
-    "gb200_logreg_midpoint_map": (C.c_int, [_P(TargetDesc), vp, vp, vp, vp, _dbl, vp, vp, vp, vp, vp, vp, vp, vp, _i64, _i64,
-                                            _i32, vp]),
-    "gb200_logreg_midpoint_map_workspace": (_i64, [_P(TargetDesc), _i64]),
-    "gb200_logreg_state_eval": (C.c_int, [_P(TargetDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, _i64, _i64, _i32, vp]),
+    "gb200_rmhmc_logreg_plan_workspace": (_i64, [_P(TargetDesc), _i64]),
+    "gb200_rmhmc_logreg_plan_create": (C.c_int, [_P(TargetDesc), _i64, vp, _i64, _i32, vp, _P(vp)]),
+    "gb200_plan_destroy": (C.c_int, [vp]),
+    "gb200_plan_loop_mode": (C.c_char_p, [vp]),
+    "gb200_plan_stats": (C.c_int, [vp, _P(_i64), _P(_i64), vp]),
+    "gb200_logreg_lockstep_eval": (C.c_int, [vp, _i32, vp, vp, vp, vp, _dbl, vp, vp, vp, vp, vp, vp, vp, vp, _i64, vp]),
     "gb200_fp32_peak_kernel": (C.c_int, [vp, _i32, _i32, _i64, vp]),
     "gb200_flops_per_chain_step": (_dbl, [_i32, _P(TargetDesc)]),
     "gb200_flops_per_transition": (_dbl, [_i32, _P(TargetDesc)]),

@@ -210,6 +210,7 @@ int gb200_step(int32_t sampler, const gb200_kernel_params* p, const gb200_target
 
   if (target->kind == GB200_TARGET_LOGREG) {
     if (sampler != GB200_RMHMC) { set_error("logreg: only rmhmc (Fisher metric) is built in this version"); return GB200_ERR_UNSUPPORTED; }
+    if (opts && opts->plan) return launch_rmhmc_lockstep(a, *target, (gb200_plan*)opts->plan, p->dtype, (cudaStream_t)stream);
     return launch_rmhmc_logreg(a, *target, p->dtype, (cudaStream_t)stream);
   }
   if (target->metric == GB200_METRIC_SOFTABS && sampler != GB200_RMHMC) {

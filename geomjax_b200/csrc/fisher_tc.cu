@@ -14,19 +14,9 @@
 // product ("3xTF32"), which keeps the metric within the 1e-5 parity budget.
 // Shared-memory operand layout = UMMA canonical K-major, no swizzle: 8-row x 16-byte core matrices,
 // [row group][k core][8 rows][16 B]: LBO (next core along K) = 128 B, SBO (next 8-row group) = KT/4*128 B.
-#include "launch.h"
+#include "fisher_tc.cuh"
 
 namespace gb {
-
-constexpr int FT_M = 128;      // pairs per CTA (MMA M)
-constexpr int FT_N = 128;      // chains per CTA (MMA N)
-constexpr int FT_KT = 32;      // data rows per stage
-constexpr int FT_KC = 4;       // stages per TMEM accumulation chunk (see the epilogue note)
-constexpr int FT_THREADS = 288;  // warps 0-7: operand producers + accumulator drainers (2 threads per pair row); warp 8: TMA / MMA issuer
-constexpr int FT_XS = FT_KT + 4;  // padded row stride (floats) of the staged X tile: conflict-free float4 row reads
-constexpr int FT_LBO = 128;                  // bytes
-constexpr int FT_SBO = (FT_KT / 4) * 128;    // bytes
-constexpr int FT_TILE_BYTES = FT_M * FT_KT * 4;
 
 __device__ __forceinline__ uint64_t ft_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -51,11 +41,6 @@ __device__ __forceinline__ void ft_mma(uint32_t tmem_d, uint64_t da, uint64_t db
 // byte offset of element (row, k) inside a canonical K-major tile
 __device__ __forceinline__ int ft_off(int row, int k) {
   return (row >> 3) * FT_SBO + (k >> 2) * FT_LBO + (row & 7) * 16 + (k & 3) * 4;
-}
-
-__device__ __forceinline__ void ft_split(float a, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);            // TF32-exact
-  lo = __uint_as_float(__float_as_uint(a - hi) & 0xFFFFE000u);       // TF32-truncated remainder
 }
 
 // ---- operand B: W^T tiles, pre-split and pre-laid-out --------------------------------------------------
@@ -139,11 +124,25 @@ __device__ __forceinline__ void ft_mbar_wait(uint32_t mbar_a, uint32_t parity) {
 // QUAD = true : h[n, chain] = sum_pair Z[n, pair] B[pair, chain]       (M = data rows, K = pairs; the 128 data rows
 //               of the CTA are staged ONCE, the pair list comes from a table; B = m_pair * A_c[i, j] pre-tiled):
 //               the quadratic forms x_n^T A_c x_n of rmhmc's dT/dq on the same pipeline.
-template <bool QUAD>
+// EPI (QUAD only): 0 = write h[c, n]; 1 = the lock-step sampler's fused epilogue (rmhmc_lockstep.cu):
+//   R[n, c] = (slot_phase[c] == END ? 0 : 1/2 w'_n quad[n, c]) - (y_n - s[c, n]),  w' = s(1-s)(1-2s),
+//   parts[m tile][i][c] = sum_{n in tile} x_ni R[n, c]   (summed over the m tiles by ls_reduce_kernel):
+//   X^T R = dT/dq - X^T(y - s), the data part of dH/dq of rmhmc's implicit-midpoint map, without h or R ever
+//   going to HBM.
+template <bool QUAD, int EPI>
 __global__ void __launch_bounds__(FT_THREADS, 1)
-fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const unsigned char* __restrict__ Wt,
-                        long long C, float alpha, float* __restrict__ G,
-                        const float* __restrict__ Xt, int ldx, const short2* __restrict__ pairs, int PS, int ldh) {
+fisher_metric_tc_kernel(const FtArgs a) {
+  const float* __restrict__ Xtile = a.Xtile;
+  const int N = a.N, D = a.D;
+  const unsigned char* __restrict__ Wt = a.Wt;
+  const long long C = a.n_active ? (long long)*a.n_active : a.C;  // lock-step sampler: chains still iterating
+  if ((long long)blockIdx.y * FT_N >= C) return;
+  const float alpha = a.alpha;
+  float* __restrict__ G = a.out;
+  const float* __restrict__ Xt = a.Xt;
+  const int ldx = a.ldx;
+  const short2* __restrict__ pairs = a.pairs;
+  const int PS = a.PS, ldh = a.ldh;
   extern __shared__ __align__(1024) unsigned char ft_smem[];
   unsigned char* Astage = ft_smem;                                  // 2 x [A_hi | A_lo]
   unsigned char* Bslot = ft_smem + 2 * 2 * FT_TILE_BYTES;           // 3 x [B_hi | B_lo] (one bulk copy each)
@@ -341,7 +340,47 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
     }
     drain(nchunks - 1);
 
-    if (QUAD) {
+    if (QUAD && EPI == 1) {
+      // every MMA has completed (the last accumulator is drained): the operand stages are free and hold R now
+      float* Rs = (float*)ft_smem;  // [128 chains][129]: conflict-free for lanes = rows (write) and lanes = chains (read)
+      const int n = m0 + row;
+      const float yn = (n < N) ? __ldg(a.y + n) : 0.f;
+#pragma unroll
+      for (int e = 0; e < NH; ++e) {  // fully unrolled: acc[] must keep static register indices
+        const long long j = c0 + half * NH + e;
+        float R = 0.f;
+        if (j < C && n < N) {
+          const float s = a.sbuf[(size_t)j * a.lds + n];
+          const float t = s * (1.f - s) * (1.f - 2.f * s) * acc[e];
+          R = (a.slot_phase[j] == LS_PH_END ? 0.f : 0.5f * t) - (yn - s);
+        }
+        Rs[(half * NH + e) * 129 + row] = R;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 producer warps (the issuer warp is not involved)
+      const int cl = tid & 127, ih = tid >> 7;
+      const int Dh = (D + 1) >> 1, i0 = ih * Dh, cnt = min(D, i0 + Dh) - i0;
+      const float* rrow = Rs + cl * 129;
+      const long long j = c0 + cl;
+      for (int ib = 0; ib < cnt; ib += 16) {  // 16 features at a time: static register indices
+        float o[16];
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) o[ii] = 0.f;
+        const float* xb = xs0 + i0 + ib;
+#pragma unroll 2
+        for (int r = 0; r < FT_M; ++r) {
+          const float rv = rrow[r];
+          const float* xrow = xb + r * DX;  // warp-uniform address: broadcast
+#pragma unroll
+          for (int ii = 0; ii < 16; ++ii)
+            if (ib + ii < cnt) o[ii] = fmaf(xrow[ii], rv, o[ii]);
+        }
+        if (j < C) {
+#pragma unroll
+          for (int ii = 0; ii < 16; ++ii)
+            if (ib + ii < cnt) a.parts[((size_t)blockIdx.x * D + i0 + ib + ii) * a.Ccap + j] = o[ii];
+        }
+      }
+    } else if (QUAD) {
       // epilogue: registers -> h[c, n] (chain-major rows of length ldh; lanes = consecutive data rows: coalesced)
       const int n = m0 + row;
       if (n < N) {
@@ -352,15 +391,20 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
         }
       }
     } else if (pi >= 0) {
-      // epilogue: registers -> G[c, i, j] (+ alpha on the diagonal)
+      // epilogue: registers -> G[c, i, j] (+ alpha on the diagonal), or packed pairs G[c, m] (lanes = consecutive
+      // pairs of one chain: coalesced)
 #pragma unroll
       for (int e = 0; e < NH; ++e) {
         const long long c = c0 + half * NH + e;
         if (c < C) {
           const float v = acc[e] + (pi == pj ? alpha : 0.f);
-          float* g = G + (size_t)c * D * D;
-          g[pi * D + pj] = v;
-          g[pj * D + pi] = v;
+          if (a.packed) {
+            G[(size_t)c * P + m0 + row] = v;
+          } else {
+            float* g = G + (size_t)c * D * D;
+            g[pi * D + pj] = v;
+            g[pj * D + pi] = v;
+          }
         }
       }
     }
@@ -372,14 +416,115 @@ fisher_metric_tc_kernel(const float* __restrict__ Xtile, int N, int D, const uns
   }
 }
 
+
+// ---- operand preparation for the quadratic forms h[c, n] = x_n^T A_c x_n -------------------------------------
+__global__ void quadform_pairs_kernel(short2* pairs, int D, int P, int PS) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= PS) return;
+  int i = 0, rem = p;
+  if (p < P) {
+    while (rem >= D - i) { rem -= D - i; ++i; }
+    pairs[p] = make_short2((short)i, (short)(i + rem));
+  } else {
+    pairs[p] = make_short2(0, 0);
+  }
+}
+// B operand: row = chain, k = pair; value = A_c[i, j] (x 2 off the diagonal), TF32 hi / lo, UMMA tile layout
+// (same thread -> address map as fisher_weights_kernel: 64 consecutive threads write one contiguous 1 KB group).
+// PACKED: A is already the packed pair vector Ap[c, P] with the off-diagonal factor applied (ls_factor_kernel).
+template <bool PACKED>
+__global__ void __launch_bounds__(256)
+quadform_b_kernel(const float* __restrict__ A, int D, int P, const short2* __restrict__ pairs, long long C_,
+                  const int* __restrict__ n_active, unsigned char* __restrict__ Bt, int ktiles, long long ctiles) {
+  const long long C = n_active ? (long long)*n_active : C_;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long tile = gid >> 10;
+  if (tile >= ctiles * ktiles) return;
+  const int l = (int)(gid & 1023);
+  const int rg = l >> 6, row = rg * 8 + (l & 7), kq = (l >> 3) & 7;
+  const long long ct = tile / ktiles;
+  if (ct * FT_N >= C) return;
+  const int kt = (int)(tile - ct * ktiles);
+  const long long c = ct * FT_N + row;
+  float w[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    if (PACKED) {
+      const float* Ac = A + (size_t)c * P;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int p = kt * FT_KT + 4 * kq + e;
+        if (p < P) w[e] = Ac[p];
+      }
+    } else {
+      const float* Ac = A + (size_t)c * D * D;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int p = kt * FT_KT + 4 * kq + e;
+        if (p < P) {
+          const short2 ij = pairs[p];
+          w[e] = Ac[ij.x * D + ij.y] * (ij.x == ij.y ? 1.f : 2.f);
+        }
+      }
+    }
+  }
+  float4 hi, lo;
+  ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
+  unsigned char* base = Bt + (size_t)tile * (2 * FT_TILE_BYTES) + (size_t)rg * FT_SBO + kq * FT_LBO + (l & 7) * 16;
+  *(float4*)base = hi;
+  *(float4*)(base + FT_TILE_BYTES) = lo;
+}
+
+// ---- launchers ------------------------------------------------------------------------------------------
+int ft_set_attributes(int D) {
+  cudaError_t e = cudaFuncSetAttribute(fisher_metric_tc_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_metric_smem(D));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(fisher_metric_tc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_quad_smem(D));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(fisher_metric_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_quad_smem(D));
+  if (e != cudaSuccess) { set_error("tcgen05 GEMM: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
+  return GB200_OK;
+}
+int ft_launch_xtile(const float* Xt, int ldx, int N, int D, float* Xtile, cudaStream_t s) {
+  const int ktiles = (N + FT_KT - 1) / FT_KT;
+  const long long total = (long long)ktiles * D * FT_XS;
+  fisher_xtile_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Xt, ldx, N, D, Xtile, ktiles);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+int ft_launch_pairs(short2* pairs, int D, cudaStream_t s) {
+  const int P = D * (D + 1) / 2, PS = ft_ps(D);
+  quadform_pairs_kernel<<<(PS + 255) / 256, 256, 0, s>>>(pairs, D, P, PS);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+int ft_launch_metric_gemm(const FtArgs& a, long long ctiles, cudaStream_t s) {
+  const int P = a.D * (a.D + 1) / 2;
+  dim3 grid((unsigned)((P + FT_M - 1) / FT_M), (unsigned)ctiles);
+  fisher_metric_tc_kernel<false, 0><<<grid, FT_THREADS, ft_metric_smem(a.D), s>>>(a);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+int ft_launch_quad_gemm(const FtArgs& a, long long ctiles, int epi, cudaStream_t s) {
+  if (ft_quad_smem(a.D) > 227 * 1024) { set_error("quadform: D=%d does not fit the staged data-row tile", a.D); return GB200_ERR_UNSUPPORTED; }
+  dim3 grid((unsigned)((a.N + FT_M - 1) / FT_M), (unsigned)ctiles);
+  if (epi) fisher_metric_tc_kernel<true, 1><<<grid, FT_THREADS, ft_quad_smem(a.D), s>>>(a);
+  else fisher_metric_tc_kernel<true, 0><<<grid, FT_THREADS, ft_quad_smem(a.D), s>>>(a);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+int ft_launch_quad_b_packed(const float* Ap, int D, long long C, const int* n_active, unsigned char* Bt, long long ctiles,
+                            cudaStream_t s) {
+  const int P = D * (D + 1) / 2, ktiles = ft_ps(D) / FT_KT;
+  const long long total = ctiles * ktiles * 1024;
+  quadform_b_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Ap, D, P, nullptr, C, n_active, Bt, ktiles, ctiles);
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+
+int fisher_metric_launch(const gb200_target_desc* t, const void* position, void* metric, void* workspace,
+                         int64_t workspace_bytes, int64_t C, int32_t dtype, float* eta_out, long long ld_eta, void* stream);
 }  // namespace gb
 
 using namespace gb;
 
-namespace gb {
-int fisher_metric_launch(const gb200_target_desc* t, const void* position, void* metric, void* workspace,
-                         int64_t workspace_bytes, int64_t C, int32_t dtype, float* eta_out, long long ld_eta, void* stream);
-}
 extern "C" int gb200_logreg_fisher_metric(const gb200_target_desc* t, const void* position, void* metric, void* workspace,
                                           int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream) {
   return gb::fisher_metric_launch(t, position, metric, workspace, workspace_bytes, C, dtype, nullptr, 0, stream);
@@ -406,71 +551,19 @@ int gb::fisher_metric_launch(const gb200_target_desc* t, const void* position, v
     GB_CHECK_LAUNCH();
   }
   float* Xtile = (float*)(Wt + wt_bytes);
-  {
-    const long long total = (long long)ktiles * D * FT_XS;
-    fisher_xtile_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float*)t->vec0, ldx, N, D, Xtile, ktiles);
-    GB_CHECK_LAUNCH();
-  }
-  const int P = D * (D + 1) / 2;
-  const size_t smem = 10 * FT_TILE_BYTES + 2 * (size_t)D * FT_XS * 4 + 1024;
-  cudaError_t e = cudaFuncSetAttribute(fisher_metric_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("fisher_metric: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
-  dim3 grid((unsigned)((P + FT_M - 1) / FT_M), (unsigned)ctiles);
-  fisher_metric_tc_kernel<false><<<grid, FT_THREADS, smem, s>>>(Xtile, N, D, Wt, C, (float)t->params[0], (float*)metric,
-                                                               nullptr, 0, nullptr, 0, 0);
-  GB_CHECK_LAUNCH();
-  return GB200_OK;
+  int rc = ft_launch_xtile((const float*)t->vec0, ldx, N, D, Xtile, s);
+  if (rc) return rc;
+  rc = ft_set_attributes(D);
+  if (rc) return rc;
+  FtArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Xtile = Xtile; a.N = N; a.D = D; a.Wt = Wt; a.C = C; a.alpha = (float)t->params[0]; a.out = (float*)metric;
+  return ft_launch_metric_gemm(a, ctiles, s);
 }
 
 // ---- quadratic forms h[c, n] = x_n^T A_c x_n for symmetric per-chain matrices A_c [C, D, D] ------------------
-namespace gb {
-__global__ void quadform_pairs_kernel(short2* pairs, int D, int P, int PS) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= PS) return;
-  int i = 0, rem = p;
-  if (p < P) {
-    while (rem >= D - i) { rem -= D - i; ++i; }
-    pairs[p] = make_short2((short)i, (short)(i + rem));
-  } else {
-    pairs[p] = make_short2(0, 0);
-  }
-}
-// B operand: row = chain, k = pair; value = A_c[i, j] (x 2 off the diagonal), TF32 hi / lo, UMMA tile layout
-// (same thread -> address map as fisher_weights_kernel: 64 consecutive threads write one contiguous 1 KB group).
-__global__ void __launch_bounds__(256)
-quadform_b_kernel(const float* __restrict__ A, int D, int P, const short2* __restrict__ pairs, long long C,
-                  unsigned char* __restrict__ Bt, int ktiles, long long ctiles) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long tile = gid >> 10;
-  if (tile >= ctiles * ktiles) return;
-  const int l = (int)(gid & 1023);
-  const int rg = l >> 6, row = rg * 8 + (l & 7), kq = (l >> 3) & 7;
-  const long long ct = tile / ktiles;
-  const int kt = (int)(tile - ct * ktiles);
-  const long long c = ct * FT_N + row;
-  float w[4] = {0.f, 0.f, 0.f, 0.f};
-  if (c < C) {
-    const float* Ac = A + (size_t)c * D * D;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int p = kt * FT_KT + 4 * kq + e;
-      if (p < P) {
-        const short2 ij = pairs[p];
-        w[e] = Ac[ij.x * D + ij.y] * (ij.x == ij.y ? 1.f : 2.f);
-      }
-    }
-  }
-  float4 hi, lo;
-  ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
-  unsigned char* base = Bt + (size_t)tile * (2 * FT_TILE_BYTES) + (size_t)rg * FT_SBO + kq * FT_LBO + (l & 7) * 16;
-  *(float4*)base = hi;
-  *(float4*)(base + FT_TILE_BYTES) = lo;
-}
-}  // namespace gb
-
 static int64_t quadform_ws(int D, int64_t C, int64_t* bt_bytes, int* PS_out) {
-  const int P = D * (D + 1) / 2;
-  const int PS = (P + FT_KT - 1) / FT_KT * FT_KT;
+  const int PS = ft_ps(D);
   const int64_t ctiles = (C + FT_N - 1) / FT_N;
   const int64_t bt = ctiles * (PS / FT_KT) * 2 * FT_TILE_BYTES;
   if (bt_bytes) *bt_bytes = bt;
@@ -498,22 +591,20 @@ extern "C" int gb200_logreg_quadform(const gb200_target_desc* t, const void* mat
   cudaStream_t s = (cudaStream_t)stream;
   unsigned char* Bt = (unsigned char*)workspace;
   short2* pairs = (short2*)(Bt + bt_bytes);
-  quadform_pairs_kernel<<<(PS + 255) / 256, 256, 0, s>>>(pairs, D, P, PS);
-  GB_CHECK_LAUNCH();
+  int rc = ft_launch_pairs(pairs, D, s);
+  if (rc) return rc;
   {
     const long long total = ctiles * ktiles * 1024;
-    quadform_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float*)matrices, D, P, pairs, C, Bt, ktiles, ctiles);
+    quadform_b_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float*)matrices, D, P, pairs, C, nullptr, Bt, ktiles, ctiles);
     GB_CHECK_LAUNCH();
   }
-  const size_t smem = 10 * FT_TILE_BYTES + (size_t)FT_M * (D | 1) * 4 + 1024;
-  if (smem > 227 * 1024) { set_error("quadform: D=%d does not fit the staged data-row tile", D); return GB200_ERR_UNSUPPORTED; }
-  cudaError_t e = cudaFuncSetAttribute(fisher_metric_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("quadform: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
-  dim3 grid((unsigned)((N + FT_M - 1) / FT_M), (unsigned)ctiles);
-  fisher_metric_tc_kernel<true><<<grid, FT_THREADS, smem, s>>>(nullptr, N, D, Bt, C, 0.f, (float*)h, (const float*)t->vec0, ldx,
-                                                              pairs, PS, (int)ldh);
-  GB_CHECK_LAUNCH();
-  return GB200_OK;
+  rc = ft_set_attributes(D);
+  if (rc) return rc;
+  FtArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = N; a.D = D; a.Wt = Bt; a.C = C; a.out = (float*)h; a.Xt = (const float*)t->vec0; a.ldx = ldx; a.pairs = pairs; a.PS = PS;
+  a.ldh = (int)ldh;
+  return ft_launch_quad_gemm(a, ctiles, 0, s);
 }
 
 extern "C" int64_t gb200_logreg_fisher_metric_workspace(const gb200_target_desc* t, int64_t C) {

@@ -1,0 +1,61 @@
+// Shared between fisher_tc.cu (the warp-specialised tcgen05 GEMMs) and rmhmc_lockstep.cu (the sampler built on them).
+#pragma once
+#include <string.h>
+#include "launch.h"
+
+namespace gb {
+
+constexpr int FT_M = 128;      // pairs (metric GEMM) / data rows (quadratic-form GEMM) per CTA: MMA M
+constexpr int FT_N = 128;      // chains per CTA (MMA N)
+constexpr int FT_KT = 32;      // K extent of one stage
+constexpr int FT_KC = 4;       // stages per TMEM accumulation chunk (see the epilogue note)
+constexpr int FT_THREADS = 288;  // warps 0-7: operand producers + accumulator drainers (2 threads per pair row); warp 8: TMA / MMA issuer
+constexpr int FT_XS = FT_KT + 4;  // padded row stride (floats) of the staged X tile: conflict-free float4 row reads
+constexpr int FT_LBO = 128;                  // bytes
+constexpr int FT_SBO = (FT_KT / 4) * 128;    // bytes
+constexpr int FT_TILE_BYTES = FT_M * FT_KT * 4;
+
+// phases of a chain in the lock-step sampler (rmhmc_lockstep.cu)
+enum { LS_PH_FIRST0 = 0, LS_PH_FIRST = 1, LS_PH_ITER = 2, LS_PH_EXPL = 3, LS_PH_END = 4, LS_PH_DONE = 5 };
+
+__device__ __forceinline__ void ft_split(float a, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);            // TF32-exact
+  lo = __uint_as_float(__float_as_uint(a - hi) & 0xFFFFE000u);       // TF32-truncated remainder
+}
+
+struct FtArgs {
+  const float* Xtile;        // metric GEMM: X re-tiled per K tile (fisher_xtile_kernel)
+  int N, D;
+  const unsigned char* Wt;   // B operand tiles (TF32 hi / lo, UMMA canonical layout), [chain tile][K tile]
+  long long C;               // chains (columns), used when n_active == NULL
+  const int* n_active;       // device: number of live columns (lock-step sampler); CTAs beyond it exit at once
+  float alpha;
+  float* out;                // metric: G [C, D, D] (packed == 0) or packed pairs [C, P]; quadratic forms: h [C, ldh]
+  int packed;
+  const float* Xt;           // quadratic forms: X^T [D, ldx]
+  int ldx;
+  const short2* pairs;
+  int PS, ldh;
+  // fused epilogue of the quadratic-form GEMM (EPI == 1)
+  const float* sbuf;         // s[c, n] = sigmoid(eta), row stride lds
+  long long lds;
+  const float* y;
+  const unsigned char* slot_phase;
+  float* parts;              // [m tiles][D][Ccap]
+  long long Ccap;
+};
+
+// launchers (fisher_tc.cu); all asynchronous on s
+int ft_launch_xtile(const float* Xt, int ldx, int N, int D, float* Xtile, cudaStream_t s);
+int ft_launch_pairs(short2* pairs, int D, cudaStream_t s);
+int ft_launch_metric_gemm(const FtArgs& a, long long ctiles, cudaStream_t s);            // vec(G) = Z^T W
+int ft_launch_quad_gemm(const FtArgs& a, long long ctiles, int epi, cudaStream_t s);     // h = Z vecsym(A)
+// packed symmetric matrices Ap[c, P] (off-diagonal entries already doubled) -> B operand tiles of the quadratic-form GEMM
+int ft_launch_quad_b_packed(const float* Ap, int D, long long C, const int* n_active, unsigned char* Bt, long long ctiles,
+                            cudaStream_t s);
+int ft_set_attributes(int D);  // cudaFuncSetAttribute for both GEMM kernels (outside stream capture)
+inline int ft_ps(int D) { const int P = D * (D + 1) / 2; return (P + FT_KT - 1) / FT_KT * FT_KT; }
+inline size_t ft_metric_smem(int D) { return 10 * (size_t)FT_TILE_BYTES + 2 * (size_t)D * FT_XS * 4 + 1024; }
+inline size_t ft_quad_smem(int D) { return 10 * (size_t)FT_TILE_BYTES + (size_t)FT_M * (D | 1) * 4 + 1024; }
+
+}  // namespace gb

@@ -26,6 +26,7 @@ inline bool lean_launch(const TransArgs& a) {
 }
 
 int launch_rmhmc_logreg(const TransArgs& a, const gb200_target_desc& t, int dtype, cudaStream_t s);
+int launch_rmhmc_lockstep(const TransArgs& a, const gb200_target_desc& t, gb200_plan* plan, int dtype, cudaStream_t s);
 int launch_init_logreg(const gb200_target_desc& t, gb200_state st, long long C, int dtype, cudaStream_t s);
 
 #define GB_BY_LPC(base, lay, ...)                          \

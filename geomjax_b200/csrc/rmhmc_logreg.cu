@@ -535,7 +535,6 @@ static int lr_setup(const gb200_target_desc& t, LogRegDev* tg, size_t* smem) {
   return GB200_OK;
 }
 
-int launch_rmhmc_logreg_tc(const TransArgs& a, const gb200_target_desc& t, cudaStream_t s);
 // rmhmc_logreg_big.cu: D > 32 or a design matrix that does not fit shared memory (X streamed from L2)
 int launch_rmhmc_logreg_big(const TransArgs& a, const gb200_target_desc& t, cudaStream_t s);
 int launch_init_logreg_big(const gb200_target_desc& t, gb200_state st, long long C, cudaStream_t s);
@@ -574,42 +573,8 @@ int launch_rmhmc_logreg(const TransArgs& a0, const gb200_target_desc& t, int dty
   a.work_count = nullptr;
   a.work_list = nullptr;
   if (lr_needs_big(t)) return launch_rmhmc_logreg_big(a, t, s);
-  // Preferred path (needs gb200_run_opts.workspace): per transition,
-  //   1. the lock-step tile kernel (rmhmc_logreg_tc.cu): both D^2 N products on tcgen05, 64 chains per CTA;
-  //      chains whose fixed point needs more than `lock_cap` iterations (the heavy tail: float32 iterates
-  //      stalling just above tol = 1e-6 run to max_iters = 100) are frozen and appended to a work list
-  //      instead of holding their whole tile hostage (which is what a vmapped while_loop does);
-  //   2. the CTA-per-chain FP32 kernel re-runs exactly those chains from their (untouched) input state
-  //      with the same keys -- same semantics, results as if every chain had been run independently.
-  // Small batches, per-chain step sizes, fused dual averaging and shapes outside the tile kernel's limits
-  // run on the CTA-per-chain kernel only.  GB200_LOGREG_TC=0 forces that, GB200_LOGREG_LOCK_CAP sets the cap.
-  static const char* env = getenv("GB200_LOGREG_TC");
-  static const char* env_cap = getenv("GB200_LOGREG_LOCK_CAP");
-  const bool allow = !(env && env[0] == '0');
-  const long long T = a.ks.keys ? 1 : a.ks.num_transitions;
-  if (allow && a.C >= 32 && a.opts.workspace != nullptr && a.opts.workspace_bytes >= 4 * a.C + 16) {
-    for (long long it = 0; it < T; ++it) {
-      TransArgs c = a;
-      c.work_count = (int*)a.opts.workspace;
-      c.work_list = c.work_count + 4;
-      c.lock_cap = env_cap ? atoi(env_cap) : 8;
-      if (a.ks.keys == nullptr) {
-        c.ks.first_transition = a.ks.first_transition + it;
-        c.ks.num_transitions = 1;
-      }
-      if (it > 0) { c.in_pos = a.out_pos; c.in_logp = a.out_logp; c.in_grad = a.out_grad; c.in_vol = a.out_vol; }
-      if (a.opts.samples) c.opts.samples = (float*)a.opts.samples + it * a.C * (long long)a.D;
-      if (a.opts.sample_accept) c.opts.sample_accept = (float*)a.opts.sample_accept + it * a.C;
-      cudaMemsetAsync(c.work_count, 0, 16, s);
-      int rc = launch_rmhmc_logreg_tc(c, t, s);
-      if (rc == GB200_ERR_UNSUPPORTED && it == 0) goto per_chain;
-      if (rc) return rc;
-      rc = launch_lr_per_chain(c, t, s);
-      if (rc) return rc;
-    }
-    return GB200_OK;
-  }
-per_chain:
+  // CTA-per-chain FP32 kernels: the path of launches WITHOUT a lock-step plan (gb200_run_opts.plan == NULL; small
+  // batches, tests).  The product path for many chains is rmhmc_lockstep.cu.
   return launch_lr_per_chain(a, t, s);
 }
 

@@ -10,8 +10,8 @@
 //     interleaved (i = bi + NBK a) so that the float4 loads along the data-row axis are bank-conflict free;
 //   * h_n = x_n^T G^-1 x_n runs as (tile x G^-1) in 8 x 4 register tiles followed by a row-wise dot product;
 //   * Cholesky, triangular inverse and G^-1 = L^-T L^-1 are CTA-wide shared-memory routines.
-// FP32 pipe only (status: correctness-first; the tcgen05 path of rmhmc_logreg_tc.cu covers D <= 28 and
-// fisher_tc.cu computes the c5-shaped metric GEMM on the tensor cores but is not fused into this sampler yet).
+// FP32 pipe only: the per-chain path for launches without a lock-step plan (small batches, tests); the product path
+// for many chains is rmhmc_lockstep.cu (both D^2 N products on the tcgen05 GEMMs of fisher_tc.cu).
 #include "launch.h"
 
 namespace gb {
@@ -618,240 +618,4 @@ int launch_init_logreg_big(const gb200_target_desc& t, gb200_state st, long long
   return GB200_OK;
 }
 
-// =====================================================================================================
-// Lock-step evaluation of the implicit-midpoint map for ALL chains at once (rmhmc/integrators.py:119-142)
-// with both D^2 N products on the warp-specialised tcgen05 GEMMs of fisher_tc.cu:
-//   pre-kernel (eta, W tiles) -> GEMM vec(G) = Z^T W -> [ls_grad_kernel: logp, gradient]
-//   -> ls_factor_kernel (CTA per chain: Cholesky, log-det, G^-1 in place, w = G^-1 p)
-//   -> GEMM h = Z vecsym(G^-1) -> ls_finish_kernel (u = X w, t = w'(h - u^2), dT = 1/2 X^T t, candidate iterate).
-// The O(N D) kernels run one CTA per chain.  A chain-tiled variant (X staged once per 32-64 chains, 64 CTAs looping over
-// all data tiles) was measured and reverted: 7.3 vs 6.8 ms per evaluation at c5's shape and 2.0 vs 1.24 s per transition
-// once the active set is compacted to a few chains (X is L2-resident; the per-chain CTAs fill the machine).  Sharing the
-// X loads between 4 chains per CTA (160 KB of shared memory, one CTA per SM) was slower as well (8.7 ms): these kernels are
-// occupancy / latency bound (5 CTAs of 41 KB per SM), not L2-bandwidth bound.
-// This is ONE evaluation of the map (the unit the fixed-point loop repeats); the sampler loop around it
-// (masked commits, accept) is the next step.
-// =====================================================================================================
-constexpr int LS_THREADS = 256;
-
-// logp[c] and grad[c, :] from eta[c, :]  (CTA per chain)
-__global__ void __launch_bounds__(LS_THREADS) ls_grad_kernel(const float* __restrict__ Xt, int ldx, const float* __restrict__ y,
-                                                             int N, int D, float alpha, const float* __restrict__ eta,
-                                                             long long ld_eta, const float* __restrict__ q,
-                                                             float* __restrict__ logp, float* __restrict__ grad) {
-  extern __shared__ float ls_sm[];  // r[N4]
-  __shared__ float red[32];
-  const long long c = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* e = eta + c * ld_eta;
-  float lp = 0.f;
-  for (int n = tid; n < N; n += LS_THREADS) {
-    const float et = e[n], yn = y[n];
-    lp += yn * et - (fmaxf(et, 0.f) + log1pf(expf(-fabsf(et))));
-    ls_sm[n] = yn - 1.f / (1.f + expf(-et));
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
-  if (lane == 0) red[warp] = lp;
-  __syncthreads();
-  if (tid == 0) {
-    float t = 0.f, qq = 0.f;
-    for (int w = 0; w < LS_THREADS / 32; ++w) t += red[w];
-    for (int i = 0; i < D; ++i) qq = fmaf(q[c * D + i], q[c * D + i], qq);
-    logp[c] = t - 0.5f * alpha * qq;
-  }
-  for (int i = warp; i < D; i += LS_THREADS / 32) {
-    float a = 0.f;
-    for (int n = lane; n < N; n += 32) a = fmaf(Xt[(size_t)i * ldx + n], ls_sm[n], a);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) grad[c * D + i] = a - alpha * q[c * D + i];
-  }
-}
-
-// CTA per chain: G[c] -> Cholesky -> log-det -> G^-1 (written back in place) and w = G^-1 p
-// z != NULL: momentum draw p = L z (rmhmc/metrics.py:45-58), written to p_out and used for w
-__global__ void __launch_bounds__(BG_THREADS, 1) ls_factor_kernel(float* __restrict__ G, const float* __restrict__ p, int D,
-                                                                  float* __restrict__ w, float* __restrict__ logdet,
-                                                                  const float* __restrict__ z, float* __restrict__ p_out) {
-  extern __shared__ __align__(128) unsigned char bg_raw[];
-  __shared__ float red[32];
-  BigLR tg;
-  tg.D = D;
-  BGSmem sm;
-  sm.G = (float*)bg_raw;
-  sm.T = sm.G + BG_ROWS * BG_LD;
-  sm.vec = sm.T + BG_ROWS * BG_LD;
-  const long long c = blockIdx.x;
-  const int tid = threadIdx.x;
-  float* Gc = G + (size_t)c * D * D;
-  for (int e = tid; e < D * D; e += BG_THREADS) sm.G[(e / D) * BG_LD + (e % D)] = Gc[e];
-  if (tid < D) sm.v(B_P)[tid] = (z != nullptr) ? z[c * D + tid] : p[c * D + tid];
-  __syncthreads();
-  const float ld = bg_cholesky(tg, sm, red);
-  if (z != nullptr) {
-    float pv = 0.f;
-    if (tid < D)
-      for (int j = 0; j <= tid; ++j) pv = fmaf(sm.G[tid * BG_LD + j], sm.v(B_P)[j], pv);
-    __syncthreads();
-    if (tid < D) {
-      sm.v(B_P)[tid] = pv;
-      p_out[c * D + tid] = pv;
-    }
-    __syncthreads();
-  }
-  bg_inverse(tg, sm);
-  bg_matvec(tg, sm, sm.v(B_P), sm.v(B_W));
-  for (int e = tid; e < D * D; e += BG_THREADS) Gc[e] = sm.G[(e / D) * BG_LD + (e % D)];
-  if (tid < D) w[c * D + tid] = sm.v(B_W)[tid];
-  if (tid == 0) logdet[c] = ld;
-}
-
-// CTA per chain: dT/dq and the candidate iterate (qn, pn) = (qi + he w, pi - he (dT - grad))
-__global__ void __launch_bounds__(LS_THREADS) ls_finish_kernel(const float* __restrict__ Xt, int ldx, int N, int D,
-                                                               const float* __restrict__ eta, const float* __restrict__ h,
-                                                               long long ld_eta, const float* __restrict__ w,
-                                                               const float* __restrict__ grad, const float* __restrict__ qi,
-                                                               const float* __restrict__ pi, float he,
-                                                               float* __restrict__ qn, float* __restrict__ pn,
-                                                               float* __restrict__ dT_out) {
-  extern __shared__ float ls_sm[];  // t[N4] then w[D]
-  const long long c = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* ws = ls_sm + (N + 3) / 4 * 4;
-  if (tid < D) ws[tid] = w[c * D + tid];
-  __syncthreads();
-  const float* e = eta + c * ld_eta;
-  const float* hc = h + c * ld_eta;
-  for (int n = tid; n < N; n += LS_THREADS) {
-    float u = 0.f;
-    for (int i = 0; i < D; ++i) u = fmaf(Xt[(size_t)i * ldx + n], ws[i], u);
-    const float s = 1.f / (1.f + expf(-e[n]));
-    ls_sm[n] = s * (1.f - s) * (1.f - 2.f * s) * (hc[n] - u * u);
-  }
-  __syncthreads();
-  for (int i = warp; i < D; i += LS_THREADS / 32) {
-    float a = 0.f;
-    for (int n = lane; n < N; n += 32) a = fmaf(Xt[(size_t)i * ldx + n], ls_sm[n], a);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) {
-      const float dT = 0.5f * a;
-      const long long k = c * D + i;
-      if (dT_out) dT_out[k] = dT;
-      qn[k] = fmaf(he, ws[i], qi[k]);
-      pn[k] = fmaf(-he, dT - grad[k], pi[k]);
-    }
-  }
-}
-
-int fisher_metric_launch(const gb200_target_desc* t, const void* position, void* metric, void* workspace,
-                         int64_t workspace_bytes, int64_t C, int32_t dtype, float* eta_out, long long ld_eta, void* stream);
-
 }  // namespace gb
-
-using namespace gb;
-
-extern "C" {
-int64_t gb200_logreg_fisher_metric_workspace(const gb200_target_desc* target, int64_t C);
-int64_t gb200_logreg_quadform_workspace(const gb200_target_desc* target, int64_t C);
-int gb200_logreg_quadform(const gb200_target_desc* target, const void* matrices, void* h, int64_t ldh, void* workspace,
-                          int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream);
-
-static int64_t ls_align(int64_t b) { return (b + 255) / 256 * 256; }
-
-int64_t gb200_logreg_midpoint_map_workspace(const gb200_target_desc* t, int64_t C) {
-  if (!t) return 0;
-  const int64_t ldn = ((int64_t)t->N + 3) / 4 * 4;
-  const int64_t gemm = ls_align(gb200_logreg_fisher_metric_workspace(t, C) > gb200_logreg_quadform_workspace(t, C)
-                                    ? gb200_logreg_fisher_metric_workspace(t, C) : gb200_logreg_quadform_workspace(t, C));
-  return gemm + 2 * ls_align(C * ldn * 4) + ls_align(C * (int64_t)t->D * t->D * 4) + 256;
-}
-
-int gb200_logreg_midpoint_map(const gb200_target_desc* t, const void* q, const void* p, const void* qi, const void* pi,
-                              double half_step, void* qn, void* pn, void* logdensity, void* logdensity_grad, void* velocity,
-                              void* logdet, void* dTdq, void* workspace, int64_t workspace_bytes, int64_t C, int32_t dtype,
-                              void* stream) {
-  if (!t || t->kind != GB200_TARGET_LOGREG) { set_error("midpoint_map: needs a logistic-regression target"); return GB200_ERR_INVALID_ARGUMENT; }
-  if (dtype != GB200_F32) { set_error("midpoint_map: float32 only"); return GB200_ERR_UNSUPPORTED; }
-  if (C == 0) return GB200_OK;
-  if (!q || !p || !qi || !pi || !qn || !pn || !logdensity || !logdensity_grad || !velocity || !logdet || !workspace || C < 0 ||
-      !t->vec0 || !t->y) { set_error("midpoint_map: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
-  const int N = (int)t->N, D = t->D, ldx = (int)t->params[1];
-  if (D > BG_DMAX) { set_error("midpoint_map: D=%d > %d", D, BG_DMAX); return GB200_ERR_UNSUPPORTED; }
-  if (workspace_bytes < gb200_logreg_midpoint_map_workspace(t, C) || ((uintptr_t)workspace & 255) != 0) {
-    set_error("midpoint_map: workspace too small or not 256-byte aligned");
-    return GB200_ERR_INVALID_ARGUMENT;
-  }
-  const int64_t ldn = ((int64_t)N + 3) / 4 * 4;
-  const int64_t fw = gb200_logreg_fisher_metric_workspace(t, C), qw = gb200_logreg_quadform_workspace(t, C);
-  const int64_t gemm = ls_align(fw > qw ? fw : qw);
-  unsigned char* b = (unsigned char*)workspace;
-  unsigned char* gemm_ws = b; b += gemm;
-  float* eta = (float*)b; b += ls_align(C * ldn * 4);
-  float* h = (float*)b; b += ls_align(C * ldn * 4);
-  float* G = (float*)b;
-  cudaStream_t s = (cudaStream_t)stream;
-  int rc = fisher_metric_launch(t, q, G, gemm_ws, gemm, C, dtype, eta, ldn, stream);
-  if (rc) return rc;
-  const size_t sm_n = (size_t)(ldn + 128) * 4;
-  cudaError_t e = cudaFuncSetAttribute(ls_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
-  const size_t sm_f = sizeof(float) * (2 * (size_t)BG_ROWS * BG_LD + BG_NV * 128) + 64;
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
-  if (e != cudaSuccess) { set_error("midpoint_map: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
-  ls_grad_kernel<<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, (const float*)t->y, N, D, (float)t->params[0], eta,
-                                                       ldn, (const float*)q, (float*)logdensity, (float*)logdensity_grad);
-  GB_CHECK_LAUNCH();
-  ls_factor_kernel<<<(unsigned)C, BG_THREADS, sm_f, s>>>(G, (const float*)p, D, (float*)velocity, (float*)logdet, nullptr, nullptr);
-  GB_CHECK_LAUNCH();
-  rc = gb200_logreg_quadform(t, G, h, ldn, gemm_ws, gemm, C, dtype, stream);
-  if (rc) return rc;
-  ls_finish_kernel<<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, N, D, eta, h, ldn, (const float*)velocity,
-                                                         (const float*)logdensity_grad, (const float*)qi, (const float*)pi,
-                                                         (float)half_step, (float*)qn, (float*)pn, (float*)dTdq);
-  GB_CHECK_LAUNCH();
-  return GB200_OK;
-}
-
-// logdensity, gradient, log det G(q) and velocity = G(q)^-1 p for all chains; with z != NULL the momentum is
-// drawn first, p = chol(G(q)) z (rmhmc/metrics.py:45-58), and written to p_out.  The pieces of a transition's
-// start and end (rmhmc/rmhmc.py:158-171) on the same pipeline as gb200_logreg_midpoint_map (no second GEMM).
-int gb200_logreg_state_eval(const gb200_target_desc* t, const void* q, const void* p, const void* z, void* p_out,
-                            void* logdensity, void* logdensity_grad, void* velocity, void* logdet, void* workspace,
-                            int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream) {
-  if (!t || t->kind != GB200_TARGET_LOGREG) { set_error("state_eval: needs a logistic-regression target"); return GB200_ERR_INVALID_ARGUMENT; }
-  if (dtype != GB200_F32) { set_error("state_eval: float32 only"); return GB200_ERR_UNSUPPORTED; }
-  if (C == 0) return GB200_OK;
-  if (!q || (!p && !z) || (z && !p_out) || !logdensity || !logdensity_grad || !velocity || !logdet || !workspace || C < 0 ||
-      !t->vec0 || !t->y) { set_error("state_eval: bad argument"); return GB200_ERR_INVALID_ARGUMENT; }
-  const int N = (int)t->N, D = t->D, ldx = (int)t->params[1];
-  if (D > BG_DMAX) { set_error("state_eval: D=%d > %d", D, BG_DMAX); return GB200_ERR_UNSUPPORTED; }
-  if (workspace_bytes < gb200_logreg_midpoint_map_workspace(t, C) || ((uintptr_t)workspace & 255) != 0) {
-    set_error("state_eval: workspace too small or not 256-byte aligned (size: gb200_logreg_midpoint_map_workspace)");
-    return GB200_ERR_INVALID_ARGUMENT;
-  }
-  const int64_t ldn = ((int64_t)N + 3) / 4 * 4;
-  const int64_t fw = gb200_logreg_fisher_metric_workspace(t, C), qw = gb200_logreg_quadform_workspace(t, C);
-  const int64_t gemm = ls_align(fw > qw ? fw : qw);
-  unsigned char* b = (unsigned char*)workspace;
-  unsigned char* gemm_ws = b; b += gemm;
-  float* eta = (float*)b; b += 2 * ls_align(C * ldn * 4);
-  float* G = (float*)b;
-  cudaStream_t s = (cudaStream_t)stream;
-  int rc = fisher_metric_launch(t, q, G, gemm_ws, gemm, C, dtype, eta, ldn, stream);
-  if (rc) return rc;
-  const size_t sm_n = (size_t)(ldn + 128) * 4;
-  cudaError_t e = cudaFuncSetAttribute(ls_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_n);
-  const size_t sm_f = sizeof(float) * (2 * (size_t)BG_ROWS * BG_LD + BG_NV * 128) + 64;
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ls_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
-  if (e != cudaSuccess) { set_error("state_eval: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
-  ls_grad_kernel<<<(unsigned)C, LS_THREADS, sm_n, s>>>((const float*)t->vec0, ldx, (const float*)t->y, N, D, (float)t->params[0], eta,
-                                                       ldn, (const float*)q, (float*)logdensity, (float*)logdensity_grad);
-  GB_CHECK_LAUNCH();
-  ls_factor_kernel<<<(unsigned)C, BG_THREADS, sm_f, s>>>(G, (const float*)p, D, (float*)velocity, (float*)logdet, (const float*)z,
-                                                         (float*)p_out);
-  GB_CHECK_LAUNCH();
-  return GB200_OK;
-}
-}  // extern "C"

@@ -129,7 +129,7 @@ class _Engine:
     def __init__(self, sampler: int, target, step_size, num_integration_steps, *,
                  divergence_threshold=1000, inverse_mass_matrix=None, alpha2=0.001,
                  half_step="omega", fp_convergence_tol=1e-6, fp_divergence_tol=1e10, fp_max_iters=100,
-                 lanes_per_chain=0):
+                 lanes_per_chain=0, logreg_path="lockstep"):
         self.sampler = sampler
         self.target = as_target(target)
         self.step_size = step_size
@@ -144,6 +144,14 @@ class _Engine:
         self.fp = (float(fp_convergence_tol), float(fp_divergence_tol), int(fp_max_iters))
         self.lanes_per_chain = int(lanes_per_chain)
         self.with_volume = sampler != N.RMHMC
+        if logreg_path not in ("lockstep", "per_chain"):
+            raise ValueError("logreg_path must be 'lockstep' or 'per_chain'")
+        self.logreg_path = logreg_path
+
+    def plan(self, chains: int, device):
+        """Lock-step plan (workspace + CUDA graph) for `chains` chains on `device`, created once and shared."""
+        from .plan import cached_plan
+        return cached_plan(self.target, chains, device)
 
     def _params(self, ref: torch.Tensor):
         p = N.KernelParams()
@@ -220,12 +228,16 @@ class _Engine:
         p, keep = self._params(q)
         desc = self.target.c_struct()
         if self.target.kind == N.TARGET_LOGREG and self.sampler == N.RMHMC:
-            # device scratch for the straggler work list of the tcgen05 lock-step path
             if opts is None:
                 opts = N.RunOpts()
-            ws = torch.empty(C_ + 4, dtype=torch.int32, device=dev)
-            keep.append(ws)
-            opts.workspace, opts.workspace_bytes = N.ptr(ws), ws.numel() * 4
+            if self.logreg_path == "lockstep" and dt == torch.float32:
+                # the product path: every map evaluation for all chains at once on the tcgen05 GEMMs
+                opts.plan = self.plan(C_, dev).handle
+            else:
+                # CTA-per-chain FP32 kernels; the scratch word is their dynamic chain hand-out counter
+                ws = torch.empty(4, dtype=torch.int32, device=dev)
+                keep.append(ws)
+                opts.workspace, opts.workspace_bytes = N.ptr(ws), ws.numel() * 4
         with torch.cuda.device(dev):
             N.check(N.lib().gb200_step(self.sampler, C.byref(p), C.byref(desc), C.byref(key_source), st_in, st_out,
                                        C.byref(info_c) if want_info else None,
@@ -359,10 +371,12 @@ class rmhmc:
     build_kernel = staticmethod(_kernel_fn(N.RMHMC, "rmhmc"))
 
     def __new__(cls, logdensity_fn, step_size, metric_fn, num_integration_steps, *,
-                divergence_threshold: int = 1000, integrator: Callable = None, lanes_per_chain: int = 0):
+                divergence_threshold: int = 1000, integrator: Callable = None, lanes_per_chain: int = 0,
+                logreg_path: str = "lockstep"):
         integ = integrators.resolve(integrators.implicit_midpoint if integrator is None else integrator, N.RMHMC)
         eng = _Engine(N.RMHMC, _merge_target(logdensity_fn, metric_fn), step_size, num_integration_steps,
-                      divergence_threshold=divergence_threshold, lanes_per_chain=lanes_per_chain, **integ.kwargs)
+                      divergence_threshold=divergence_threshold, lanes_per_chain=lanes_per_chain,
+                      logreg_path=logreg_path, **integ.kwargs)
         return SamplingAlgorithm(lambda position: cls.init(position, eng.target), _StepFn(eng))
 
 

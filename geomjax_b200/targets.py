@@ -68,35 +68,6 @@ class TargetDescriptor:
                                                   A.shape[0], N.F32, N.stream_ptr()))
         return h
 
-    def midpoint_map(self, q, p, qi, pi, half_step: float):
-        """One lock-step evaluation of rmhmc's implicit-midpoint map for all chains (rmhmc/integrators.py:119-142) on the
-        logistic-regression target with both D^2 N products on tcgen05.  Returns a dict with ``q``, ``p`` (the new
-        iterate), ``logdensity``, ``logdensity_grad``, ``velocity`` (= G^-1 p), ``logdet`` and ``dTdq``."""
-        import ctypes as C
-        import torch
-        if self.kind != N.TARGET_LOGREG:
-            raise NotImplementedError("midpoint_map() is built for the logistic-regression target")
-        f = lambda t: t.to(torch.float32).contiguous()
-        q, p, qi, pi = f(q), f(p), f(qi), f(pi)
-        C_, D = q.shape
-        if D != self.D or p.shape != q.shape or qi.shape != q.shape or pi.shape != q.shape:
-            raise ValueError(f"q, p, qi, pi must all have shape (C, {self.D})")
-        d = self.c_struct()
-        ws_bytes = N.lib().gb200_logreg_midpoint_map_workspace(C.byref(d), C_)
-        ws = torch.empty(int(ws_bytes) // 4 + 64, dtype=torch.float32, device=q.device)
-        off = (-ws.data_ptr()) % 256
-        wsp = ws.data_ptr() + off
-        out = {k: torch.empty_like(q) for k in ("q", "p", "logdensity_grad", "velocity", "dTdq")}
-        out.update({k: torch.empty(C_, dtype=torch.float32, device=q.device) for k in ("logdensity", "logdet")})
-        with torch.cuda.device(q.device):
-            N.check(N.lib().gb200_logreg_midpoint_map(C.byref(d), N.ptr(q), N.ptr(p), N.ptr(qi), N.ptr(pi), float(half_step),
-                                                      N.ptr(out["q"]), N.ptr(out["p"]), N.ptr(out["logdensity"]),
-                                                      N.ptr(out["logdensity_grad"]), N.ptr(out["velocity"]),
-                                                      N.ptr(out["logdet"]), N.ptr(out["dTdq"]), C.c_void_p(wsp), ws_bytes, C_,
-                                                      N.F32, N.stream_ptr()))
-        out["_workspace"] = ws
-        return out
-
     def with_metric(self, metric: str) -> "TargetDescriptor":
         """``metric='identity'`` == ``metric_fn=lambda x: jnp.eye(D)`` (tests/test_samplers.py:25)."""
         m = {"target": N.METRIC_TARGET, "identity": N.METRIC_IDENTITY}[metric]

@@ -154,9 +154,11 @@ typedef struct gb200_run_opts {
                                   (optimizers/dual_averaging.py:101-123); step size = exp(log_x) */
   double da_target;            /* target acceptance rate (adaptation/step_size_adaptation.py:103) */
   double da_t0, da_gamma, da_kappa; /* (10, 0.05, 0.75) */
-  void* workspace;             /* optional device scratch; >= 4*C + 16 bytes enables the tcgen05 lock-step path of
-                                  rmhmc on the logistic-regression target (straggler work list) */
+  void* workspace;             /* optional device scratch (>= 16 bytes): dynamic chain hand-out of the CTA-per-chain
+                                  logistic-regression kernels (used when plan == NULL) */
   int64_t workspace_bytes;
+  void* plan;                  /* gb200_plan* (below): rmhmc on the logistic-regression target runs the lock-step
+                                  tcgen05 sampler */
 } gb200_run_opts;
 
 int gb200_version(void);
@@ -234,22 +236,35 @@ int64_t gb200_logreg_fisher_metric_workspace(const gb200_target_desc* target, in
 int gb200_logreg_quadform(const gb200_target_desc* target, const void* matrices, void* h, int64_t ldh, void* workspace,
                           int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream);
 int64_t gb200_logreg_quadform_workspace(const gb200_target_desc* target, int64_t C);
-/* ONE evaluation of rmhmc's implicit-midpoint map (rmhmc/integrators.py:119-142) for ALL chains in lock-step on the
- * logistic-regression target, both D^2 N products on the tcgen05 GEMMs above:
- *   (qn, pn) = (qi + h dH/dp(q, p), pi - h dH/dq(q, p)),  h = half_step,
- *   dH/dp = G(q)^-1 p (-> velocity),  dH/dq = dT/dq - grad logp  (-> logdensity, logdensity_grad, logdet G, dTdq).
- * All arrays [C, D] / [C] float32; dTdq may be NULL.  The unit a lock-step fixed-point loop repeats. */
-int gb200_logreg_midpoint_map(const gb200_target_desc* target, const void* q, const void* p, const void* qi, const void* pi,
-                              double half_step, void* qn, void* pn, void* logdensity, void* logdensity_grad, void* velocity,
-                              void* logdet, void* dTdq, void* workspace, int64_t workspace_bytes, int64_t C, int32_t dtype,
-                              void* stream);
-int64_t gb200_logreg_midpoint_map_workspace(const gb200_target_desc* target, int64_t C);
-/* Start / end of a transition on the same pipeline (rmhmc/rmhmc.py:158-171): logdensity, gradient, log det G(q) and
- * velocity = G(q)^-1 p for all chains; with z != NULL the momentum p = chol(G(q)) z is drawn first and written to
- * p_out (rmhmc/metrics.py:45-58).  Workspace size: gb200_logreg_midpoint_map_workspace. */
-int gb200_logreg_state_eval(const gb200_target_desc* target, const void* q, const void* p, const void* z, void* p_out,
-                            void* logdensity, void* logdensity_grad, void* velocity, void* logdet, void* workspace,
-                            int64_t workspace_bytes, int64_t C, int32_t dtype, void* stream);
+/* ---- rmhmc on the logistic-regression target: the lock-step "rolling batch" sampler ---------------------------
+ * rmhmc/rmhmc.py:131-174 (+416-462), rmhmc/integrators.py:53-156 under vmap.  Every evaluation of the
+ * implicit-midpoint map runs for ALL unfinished chains at once with both D^2 N products on the tcgen05 GEMMs
+ * above; each chain carries its own (transition, step, fixed-point iteration) state, so chains that converge early
+ * move on (to their next step, or their next transition of a fused launch) instead of idling behind the slowest
+ * chain as a vmapped while_loop makes them.  The round is the body of a CUDA-graph WHILE node: gb200_step stays
+ * asynchronous.  A plan owns the graph and borrows caller memory:
+ *   workspace: >= gb200_rmhmc_logreg_plan_workspace(target, C) bytes, 256-byte aligned, alive until plan_destroy;
+ *   loop_mode: 0 = device-side WHILE node (falls back to 1 if the driver refuses it; see gb200_plan_loop_mode),
+ *              1 = host-sequenced rounds (gb200_step then blocks the calling thread on its own stream).
+ * Pass the plan in gb200_run_opts.plan to gb200_step / gb200_rmhmc_step (C <= the plan's C, same target). */
+typedef struct gb200_plan gb200_plan;
+int64_t gb200_rmhmc_logreg_plan_workspace(const gb200_target_desc* target, int64_t C);
+int gb200_rmhmc_logreg_plan_create(const gb200_target_desc* target, int64_t C, void* workspace, int64_t workspace_bytes,
+                                   int32_t loop_mode, void* stream, gb200_plan** out);
+int gb200_plan_destroy(gb200_plan* plan);
+const char* gb200_plan_loop_mode(const gb200_plan* plan);
+/* rounds and chain-evaluations of the plan's last launch (synchronises the stream; measurement only) */
+int gb200_plan_stats(const gb200_plan* plan, int64_t* rounds, int64_t* chain_evals, void* stream);
+/* ONE round for explicit inputs (test surface; the unit the sampler's loop repeats), all arrays [C, D] / [C] float32:
+ *   mode 0: the implicit-midpoint map (rmhmc/integrators.py:119-142) at (q, p) from (qi, pi):
+ *           qn = qi + h dH/dp, pn = pi - h dH/dq, h = half_step; velocity = dH/dp = G(q)^-1 p, logdet = log det G(q),
+ *           dHdq = dT/dq - grad logp;
+ *   mode 1: end-of-trajectory state (rmhmc/integrators.py:150-154): logdensity, logdensity_grad, velocity, logdet;
+ *   mode 2: mode 0 with the momentum drawn first: p holds z, p_out = chol(G(q)) z (rmhmc/metrics.py:45-58), pi = p_out.
+ * Outputs may be NULL. */
+int gb200_logreg_lockstep_eval(gb200_plan* plan, int32_t mode, const void* q, const void* p, const void* qi, const void* pi,
+                               double half_step, void* qn, void* pn, void* p_out, void* logdensity, void* logdensity_grad,
+                               void* velocity, void* logdet, void* dHdq, int64_t C, void* stream);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Runs a dependent-FMA microbenchmark (iters FFMA per thread on grid x block threads) for the FP32

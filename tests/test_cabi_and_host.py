@@ -132,11 +132,19 @@ def test_bench_reference_arm_contract():
     assert "workload" in line["config"] and line["gpu_launches"] == 0
 
 
-def test_lockstep_facade_rejects_other_targets():
-    """rmhmc_lockstep is built for the logistic-regression target; anything else is refused up front."""
+def test_lockstep_plan_rejects_other_targets():
+    """The lock-step plan is built for the logistic-regression target; anything else is refused up front."""
     import geomjax_b200 as g
-    t = g.neal_funnel(4)
     with pytest.raises(NotImplementedError):
-        g.rmhmc_lockstep(t, 0.1, t, 4)
-    with pytest.raises(NotImplementedError):
-        g.rmhmc_lockstep(lambda x: 0.0, 0.1, None, 4)
+        g.LockstepPlan(g.neal_funnel(4), 8, "cpu")
+    with pytest.raises(ValueError):
+        g.rmhmc(g.neal_funnel(4), 0.1, g.neal_funnel(4), 4, logreg_path="nope")
+
+
+def test_bench_data_equals_the_oracle_generator():
+    from bench.data import make_logreg_data
+    from oracle.targets import make_logreg_data as ref
+    for N_, D_, seed in [(40, 3, 0), (1000, 25, 0), (333, 17, 4)]:
+        X, y = make_logreg_data(N_, D_, seed)
+        Xo, yo = ref(N_, D_, seed)
+        assert (X == Xo).all() and (y == yo).all()

@@ -23,7 +23,10 @@ def _close(got, want, rtol, atol, what=""):
                                           (40, 3, 64, 1), (200, 8, 40, 2), (1000, 25, 70, 1), (1000, 25, 33, 2), (333, 17, 65, 2),
                                           # rmhmc_logreg_big.cu: D > 32 or X larger than shared memory; last = c5's shape
                                           (300, 40, 5, 2), (50, 33, 4, 1), (4000, 30, 3, 1), (10000, 100, 3, 1)])
-def test_rmhmc_logreg_vs_oracle(cuda, Nrows, D, C, L):
+@pytest.mark.parametrize("path", ["lockstep", "per_chain"])
+def test_rmhmc_logreg_vs_oracle(cuda, Nrows, D, C, L, path):
+    """`path` = the product path (lock-step rolling batch on the tcgen05 GEMMs, rmhmc_lockstep.cu) and the
+    CTA-per-chain FP32 kernels kept beside it (rmhmc_logreg.cu / rmhmc_logreg_big.cu)."""
     import geomjax_b200 as g
     X, y = T.make_logreg_data(Nrows, D, seed=1)
     tgt = T.LogisticRegression(X, y, 0.01)
@@ -35,7 +38,7 @@ def test_rmhmc_logreg_vs_oracle(cuda, Nrows, D, C, L):
     ost = S.rmhmc_init(q, tgt)
     onew, oinfo = S.rmhmc_step(keys, ost, tgt, eps, L)
     target = g.logistic_regression(_t(X, cuda), _t(y, cuda), 0.01)
-    alg = g.rmhmc(target, eps, target, L)
+    alg = g.rmhmc(target, eps, target, L, logreg_path=path)
     st = alg.init(_t(q, cuda))
     _close(st.logdensity, ost.logdensity, 1e-5, 1e-3, "init logdensity")
     _close(st.logdensity_grad, ost.logdensity_grad, 1e-4, 1e-3, "init grad")
@@ -168,8 +171,10 @@ def test_lockstep_midpoint_map_vs_oracle(cuda, Nrows, D, C):
     dT64, v64 = S._rmhmc_kinetic_grad(t64, q.astype(np.float64), p.astype(np.float64))
     g64 = t64.grad(q.astype(np.float64))
     target = g.logistic_regression(_t(X, cuda), _t(y, cuda), 0.01)
-    out = target.midpoint_map(_t(q, cuda), _t(p, cuda), _t(qi, cuda), _t(pi, cuda), he)
-    n = lambda k: out[k].cpu().numpy().astype(np.float64)
+    plan = g.LockstepPlan(target, C, cuda)
+    out = plan.evaluate(0, _t(q, cuda), _t(p, cuda), _t(qi, cuda), _t(pi, cuda), he)
+    end = plan.evaluate(1, _t(q, cuda), _t(p, cuda))
+    n = lambda k: (end if k in ("logdensity", "logdensity_grad") else out)[k].cpu().numpy().astype(np.float64)
     vs = np.abs(v64).max(axis=1, keepdims=True)
     assert (np.abs(n("velocity") - v64) / vs).max() < 2e-4
     gs = np.abs(g64).max(axis=1, keepdims=True)
@@ -177,44 +182,10 @@ def test_lockstep_midpoint_map_vs_oracle(cuda, Nrows, D, C):
     np.testing.assert_allclose(n("logdensity"), t64.logp(q.astype(np.float64)), rtol=2e-5)
     np.testing.assert_allclose(n("logdet"), np.linalg.slogdet(t64.metric(q.astype(np.float64)))[1], rtol=1e-5, atol=1e-3)
     ds = np.abs(dT64).max(axis=1, keepdims=True)
-    assert (np.abs(n("dTdq") - dT64) / ds).max() < 5e-4
+    dH64 = dT64 - g64
+    assert (np.abs(n("dHdq") - dH64) / np.maximum(ds, gs)).max() < 5e-4
+    assert (np.abs(end["velocity"].cpu().numpy() - v64) / vs).max() < 2e-4
     qn64 = qi.astype(np.float64) + he * v64
     pn64 = pi.astype(np.float64) - he * (dT64 - g64)
     assert (np.abs(n("q") - qn64) / np.abs(qn64).max(axis=1, keepdims=True)).max() < 2e-4
     assert (np.abs(n("p") - pn64) / np.abs(pn64).max(axis=1, keepdims=True)).max() < 2e-4
-
-
-@pytest.mark.parametrize("Nrows,D,C,L", [(200, 8, 40, 2), (1000, 25, 70, 2), (10000, 100, 4, 1)])
-def test_rmhmc_lockstep_vs_oracle(cuda, Nrows, D, C, L):
-    """rmhmc with every map evaluation run for all chains in lock-step on the tcgen05 GEMMs (rmhmc_lockstep)
-    against the oracle: same keys, same masked fixed-point semantics."""
-    import geomjax_b200 as g
-    X, y = T.make_logreg_data(Nrows, D, seed=1)
-    tgt = T.LogisticRegression(X, y, 0.01)
-    tgt.structured_dmetric = Nrows * D ** 3 > 1e9
-    rng = np.random.default_rng(D)
-    q = (0.1 * rng.standard_normal((C, D))).astype(np.float32)
-    keys = rng.integers(0, 2 ** 32, size=(C, 2), dtype=np.uint64).astype(np.uint32)
-    eps = 0.1 if D <= 40 else 0.05
-    ost = S.rmhmc_init(q, tgt)
-    onew, oinfo = S.rmhmc_step(keys, ost, tgt, eps, L)
-    target = g.logistic_regression(_t(X, cuda), _t(y, cuda), 0.01)
-    alg = g.rmhmc_lockstep(target, eps, target, L)
-    st = alg.init(_t(q, cuda))
-    new, info = alg.step(_t(keys, cuda), st)
-    ok = oinfo.extra["fp_iters"] < 50 * L
-    assert oinfo.is_accepted.mean() > 0.5 and ok.mean() > 0.7
-    okt = _t(ok, cuda)
-    scale = float(np.abs(oinfo.momentum).max())
-    _close(info.momentum, oinfo.momentum, 1e-5, 5e-5 * scale, "momentum draw")
-    ps = info.proposal.state
-    _close(ps.position[okt], oinfo.proposal["position"][ok], 1e-4, 2e-5, "position")
-    _close(ps.momentum[okt], oinfo.proposal["momentum"][ok], 1e-4, 2e-4 * scale, "momentum")
-    _close(ps.logdensity[okt], oinfo.proposal["logdensity"][ok], 1e-5, 3e-3, "logdensity")
-    _close(info.energy[okt], oinfo.energy[ok], 1e-5, 5e-3, "energy")
-    _close(info.acceptance_rate[okt], oinfo.acceptance_rate[ok], 1e-2, 1e-2, "acceptance")
-    got_acc = info.is_accepted.cpu().numpy()
-    clear = np.abs(oinfo.extra["u"] - oinfo.acceptance_rate) > 3e-2
-    np.testing.assert_array_equal(got_acc[clear & ok], oinfo.is_accepted[clear & ok])
-    same = (got_acc == oinfo.is_accepted) & ok
-    _close(new.position[_t(same, cuda)], onew.position[same], 1e-4, 2e-5)
