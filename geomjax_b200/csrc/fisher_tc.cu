@@ -109,6 +109,49 @@ __device__ __forceinline__ void ft_mbar_wait(uint32_t mbar_a, uint32_t parity) {
   }
 }
 
+// Fused epilogue of the quadratic-form GEMM (EPI == 1): out[i, c] = sum_r x[r, i] R[r, c] over the CTA's 128 data rows.
+// Thread tile = TI features x TC chains (chains cb + (128 / TC) k: lanes read consecutive rows of Rs[c][129], no bank
+// conflicts; the x reads are broadcasts), TI + TC shared-memory loads per TI * TC FMAs.
+template <int TI, int TC>
+__device__ __forceinline__ void ft_epi_xtr(const float* __restrict__ xr, int DX, const float* __restrict__ Rs, int D,
+                                           float* __restrict__ parts, long long Ccap, long long c0, long long C, int tid) {
+  constexpr int CB = FT_N / TC;
+  const int cb = tid % CB, ib = tid / CB;
+  if (ib * TI >= D) return;
+  int fi[TI];
+#pragma unroll
+  for (int t = 0; t < TI; ++t) fi[t] = min(ib * TI + t, D - 1);
+  float o[TI][TC];
+#pragma unroll
+  for (int t = 0; t < TI; ++t)
+#pragma unroll
+    for (int k = 0; k < TC; ++k) o[t][k] = 0.f;
+  const float* rp = Rs + cb * 129;
+#pragma unroll 4
+  for (int r = 0; r < FT_M; ++r) {
+    float xv[TI], rv[TC];
+#pragma unroll
+    for (int t = 0; t < TI; ++t) xv[t] = xr[r * DX + fi[t]];
+#pragma unroll
+    for (int k = 0; k < TC; ++k) rv[k] = rp[(CB * k) * 129 + r];
+#pragma unroll
+    for (int t = 0; t < TI; ++t)
+#pragma unroll
+      for (int k = 0; k < TC; ++k) o[t][k] = fmaf(xv[t], rv[k], o[t][k]);
+  }
+#pragma unroll
+  for (int t = 0; t < TI; ++t) {
+    const int i = ib * TI + t;
+    if (i < D) {
+#pragma unroll
+      for (int k = 0; k < TC; ++k) {
+        const long long j = c0 + cb + CB * k;
+        if (j < C) parts[(size_t)i * Ccap + j] = o[t][k];
+      }
+    }
+  }
+}
+
 // ---- the GEMM: warp-specialised, two A stages, three B slots, two TMEM accumulators -----------------------
 // Producers (warps 0-7; thread pair = pair row = TMEM lane, each thread half of the K range and half of the
 // accumulator columns), per K tile kt (32 data rows):
@@ -357,29 +400,10 @@ fisher_metric_tc_kernel(const FtArgs a) {
         Rs[(half * NH + e) * 129 + row] = R;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 producer warps (the issuer warp is not involved)
-      const int cl = tid & 127, ih = tid >> 7;
-      const int Dh = (D + 1) >> 1, i0 = ih * Dh, cnt = min(D, i0 + Dh) - i0;
-      const float* rrow = Rs + cl * 129;
-      const long long j = c0 + cl;
-      for (int ib = 0; ib < cnt; ib += 16) {  // 16 features at a time: static register indices
-        float o[16];
-#pragma unroll
-        for (int ii = 0; ii < 16; ++ii) o[ii] = 0.f;
-        const float* xb = xs0 + i0 + ib;
-#pragma unroll 2
-        for (int r = 0; r < FT_M; ++r) {
-          const float rv = rrow[r];
-          const float* xrow = xb + r * DX;  // warp-uniform address: broadcast
-#pragma unroll
-          for (int ii = 0; ii < 16; ++ii)
-            if (ib + ii < cnt) o[ii] = fmaf(xrow[ii], rv, o[ii]);
-        }
-        if (j < C) {
-#pragma unroll
-          for (int ii = 0; ii < 16; ++ii)
-            if (ib + ii < cnt) a.parts[((size_t)blockIdx.x * D + i0 + ib + ii) * a.Ccap + j] = o[ii];
-        }
-      }
+      // parts[m tile][i][c] = sum_r x[r, i] R[r, c]: a 128 x D x 128 product on the FP32 pipe, register-tiled
+      float* pbase = a.parts + (size_t)blockIdx.x * D * a.Ccap;
+      if (D <= 32) ft_epi_xtr<4, 4>(xs0, DX, Rs, D, pbase, a.Ccap, c0, C, tid);
+      else ft_epi_xtr<8, 8>(xs0, DX, Rs, D, pbase, a.Ccap, c0, C, tid);
     } else if (QUAD) {
       // epilogue: registers -> h[c, n] (chain-major rows of length ldh; lanes = consecutive data rows: coalesced)
       const int n = m0 + row;

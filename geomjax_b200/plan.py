@@ -6,6 +6,7 @@ csrc/rmhmc_lockstep.cu.  PyTorch only supplies the device memory."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 
 import torch
@@ -26,7 +27,9 @@ def cached_plan(target, chains: int, device) -> "LockstepPlan":
            tuple(float(x) for x in target.params), int(chains), dev.index)
     pl = _PLANS.pop(key, None)
     if pl is None:
-        pl = LockstepPlan(target, chains, dev)
+        # GEOMB200_LOCKSTEP_LOOP=1: host-sequenced rounds instead of the graph WHILE node (profilers that cannot
+        # see inside conditional graph nodes); read once per plan, never on the launch path
+        pl = LockstepPlan(target, chains, dev, loop_mode=int(os.environ.get("GEOMB200_LOCKSTEP_LOOP", "0")))
         while len(_PLANS) >= _MAX_PLANS:
             _PLANS.pop(next(iter(_PLANS)))
     _PLANS[key] = pl  # most recently used last
