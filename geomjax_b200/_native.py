@@ -64,7 +64,7 @@ class RunOpts(C.Structure):
     _fields_ = [("samples", vp), ("sample_accept", vp), ("noise_override", vp), ("uniform_override", vp),
                 ("dual_averaging", vp), ("da_target", C.c_double), ("da_t0", C.c_double),
                 ("da_gamma", C.c_double), ("da_kappa", C.c_double),
-                ("workspace", vp), ("workspace_bytes", C.c_int64), ("plan", vp)]
+                ("workspace", vp), ("workspace_bytes", C.c_int64), ("plan", vp), ("accept_sum", vp)]
 
 
 _i32, _i64, _dbl = C.c_int32, C.c_int64, C.c_double

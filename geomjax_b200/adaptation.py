@@ -50,6 +50,7 @@ def dual_averaging(t0: int = 10, gamma: float = 0.05, kappa: float = 0.75):
         return DualAveragingState(da[:, 0], da[:, 1], da[:, 2], da[:, 3], da[:, 4])
 
     def init(x_init: torch.Tensor) -> DualAveragingState:
+        _require_f32(x_init)
         x = x_init.contiguous()
         da = torch.empty((x.shape[0], 5), dtype=x.dtype, device=x.device)
         with torch.cuda.device(x.device):
@@ -94,6 +95,13 @@ def _engine_for(algorithm, logdensity_fn, step_size, extra):
     raise NotImplementedError("adaptation is available for geomjax_b200.rmhmc, lmc and lmcmonge")
 
 
+def _require_f32(position):
+    # the fused dual-averaging epilogue indexes its state in the chain state's dtype; the drivers keep float32
+    # adaptation state, so float64 chains are refused here (and by gb200_step) instead of being mis-read
+    if position.dtype != torch.float32:
+        raise TypeError(f"adaptation runs on float32 chains; got {position.dtype}")
+
+
 def _da_init(C, eps0, device):
     da = torch.empty((C, 5), dtype=torch.float32, device=device)
     x = torch.full((C,), float(eps0), dtype=torch.float32, device=device)
@@ -125,6 +133,7 @@ def step_size_adaptation(algorithm, logdensity_fn, initial_step_size: float = 1.
     del progress_bar  # host UI of the reference (fastprogress through host_callback); no-op here
 
     def run(rng_key, position: torch.Tensor, num_steps: int = 1000):
+        _require_f32(position)
         C_ = position.shape[0]
         dev = position.device
         eng = _engine_for(algorithm, logdensity_fn, initial_step_size, extra_parameters)
@@ -162,34 +171,34 @@ def step_size_adaptation(algorithm, logdensity_fn, initial_step_size: float = 1.
     return AdaptationAlgorithm(run)
 
 
+def _slow_windows(start: int, stop: int, first: int):
+    """End indices (exclusive) of the doubling slow windows that tile [start, stop): a window doubles as long as
+    the one after it would still fit three of itself; the last one absorbs the remainder."""
+    ends, size = [], first
+    while start < stop:
+        if stop - start >= 3 * size:
+            start, size = start + size, 2 * size
+        else:
+            start = stop
+        ends.append(start)
+    return ends
+
+
 def build_schedule(num_steps: int, initial_buffer_size: int = 75, final_buffer_size: int = 50,
                    first_window_size: int = 25):
-    """adaptation/window_adaptation.py:360-450 (Stan's fast / slow / fast windows)."""
-    schedule = []
-    if num_steps < 20:
-        schedule += [(0, False)] * num_steps
-    else:
-        if initial_buffer_size + first_window_size + final_buffer_size > num_steps:
-            initial_buffer_size = int(0.15 * num_steps)
-            final_buffer_size = int(0.1 * num_steps)
-            first_window_size = num_steps - initial_buffer_size - final_buffer_size
-        schedule += [(0, False)] * (initial_buffer_size - 1)
-        schedule.append((0, False))
-        final_buffer_start = num_steps - final_buffer_size
-        next_window_size = first_window_size
-        next_window_start = initial_buffer_size
-        while next_window_start < final_buffer_start:
-            current_start, current_size = next_window_start, next_window_size
-            if 3 * current_size <= final_buffer_start - current_start:
-                next_window_size = 2 * current_size
-            else:
-                current_size = final_buffer_start - current_start
-            next_window_start = current_start + current_size
-            schedule += [(1, False)] * (next_window_start - 1 - current_start)
-            schedule.append((1, True))
-        schedule += [(0, False)] * (num_steps - 1 - final_buffer_start)
-        schedule.append((0, False))
-    return schedule
+    """Stan's fast / slow / fast warm-up schedule as a list of ``(stage, is_middle_window_end)`` per transition:
+    stage 0 = step size only, stage 1 = step size + mass matrix, the flag marks the last transition of a slow
+    window.  Same list as adaptation/window_adaptation.py:360-450 (checked element by element against the oracle's
+    restatement in tests/test_cabi_and_host.py)."""
+    if num_steps < 20:  # too short for mass-matrix adaptation
+        return [(0, False)] * num_steps
+    if initial_buffer_size + first_window_size + final_buffer_size > num_steps:
+        initial_buffer_size, final_buffer_size = int(0.15 * num_steps), int(0.1 * num_steps)
+        first_window_size = num_steps - initial_buffer_size - final_buffer_size
+    slow_stop = num_steps - final_buffer_size
+    window_ends = set(_slow_windows(initial_buffer_size, slow_stop, first_window_size))
+    return [(1, (t + 1) in window_ends) if initial_buffer_size <= t < slow_stop else (0, False)
+            for t in range(num_steps)]
 
 
 def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = True,
@@ -206,6 +215,7 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
         raise ValueError("The mass matrix has the wrong number of dimensions: expected 1, got 2.")  # lmcmonge/metrics.py:148-153
 
     def run(rng_key, position: torch.Tensor, num_steps: int = 1000):
+        _require_f32(position)
         C_, D = position.shape
         dev = position.device
         inv_mass = torch.ones((C_, D), dtype=torch.float32, device=dev)  # mm_init mass_matrix.py:95-100

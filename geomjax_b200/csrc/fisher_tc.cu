@@ -4,11 +4,11 @@
 // P = D(D+1)/2 pairs i <= j.  This is `metric_fn` of the logistic-regression target under vmap
 // (what rmhmc/metrics.py:46,62,121 call at every evaluation).
 //
-// tcgen05 mapping (one CTA = 128 pairs x 128 chains, accumulators in TMEM):
+// tcgen05 mapping (one CTA = 128 pairs x 256 chains, accumulators in TMEM):
 //   A = Z^T tile  [M = 128 pairs ,  K = data rows]  K-major, built ON THE FLY in shared memory from a
 //                 staged X tile (Z is never materialised: it would be N x P floats),
-//   B = W^T tile  [N = 128 chains,  K = data rows]  K-major,
-//   D = 128 lanes x 128 columns of FP32 in tensor memory, read back with tcgen05.ld.
+//   B = W^T tile  [N = 256 chains,  K = data rows]  K-major,
+//   D = 128 lanes x 256 columns of FP32 in tensor memory, read back with tcgen05.ld.
 // Precision: tcgen05 has no FP32 MMA.  Each operand is split into a TF32-exact high part and the
 // TF32-truncated remainder; three MMAs (hi*hi + hi*lo + lo*hi) give ~2^-21 relative error per
 // product ("3xTF32"), which keeps the metric within the 1e-5 parity budget.
@@ -27,7 +27,7 @@ __device__ __forceinline__ uint64_t ft_smem_desc(uint32_t saddr) {
   return d;                                           // layout_type = 0 (no swizzle), base_offset = 0
 }
 
-// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 128
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 256
 constexpr uint32_t FT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(FT_N >> 3) << 17) | ((uint32_t)(FT_M >> 4) << 24);
 
 __device__ __forceinline__ void ft_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
@@ -45,19 +45,19 @@ __device__ __forceinline__ int ft_off(int row, int k) {
 
 // ---- operand B: W^T tiles, pre-split and pre-laid-out --------------------------------------------------
 // w[c, n] = s(1-s), s = sigmoid(x_n . theta_c), written ONCE per call as TF32 hi / lo parts directly in the
-// UMMA canonical K-major tile layout, one 32 KB block per (chain tile of 128, K tile of 32 data rows):
+// UMMA canonical K-major tile layout, one 32 KB block per (chain tile of 256, K tile of 16 data rows):
 // [hi tile 16 KB][lo tile 16 KB].  The GEMM kernel then fetches a B stage with ONE bulk-TMA copy instead
 // of 128 threads issuing 32 scattered loads + splits each.  One thread = (chain, 4 consecutive data rows)
-// = one 16-byte core-matrix row; 64 consecutive threads write one contiguous 1 KB row group.
+// = one 16-byte core-matrix row; 32 consecutive threads write one contiguous 512-byte row group.
 __global__ void __launch_bounds__(256)
 fisher_weights_kernel(const float* __restrict__ Xt, int ldx, int N, int D, const float* __restrict__ theta,
                       long long C, unsigned char* __restrict__ Wt, int ktiles, long long ctiles,
                       float* __restrict__ eta_out, long long ld_eta) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long tile = gid >> 10;  // 1024 threads per (chain tile, K tile): 128 rows x 8 k-quads
+  const long long tile = gid >> 10;  // 1024 threads per (chain tile, K tile): 256 rows x 4 k-quads
   if (tile >= ctiles * ktiles) return;
   const int l = (int)(gid & 1023);
-  const int rg = l >> 6, row = rg * 8 + (l & 7), kq = (l >> 3) & 7;
+  const int rg = l >> 5, row = rg * 8 + (l & 7), kq = (l >> 3) & 3;  // a warp = one 8-row group = 512 contiguous bytes
   const long long ct = tile / ktiles;
   const int kt = (int)(tile - ct * ktiles);
   const long long c = ct * FT_N + row;
@@ -81,9 +81,9 @@ fisher_weights_kernel(const float* __restrict__ Xt, int ldx, int N, int D, const
   }
   float4 hi, lo;
   ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
-  unsigned char* base = Wt + (size_t)tile * (2 * FT_TILE_BYTES) + (size_t)rg * FT_SBO + kq * FT_LBO + (l & 7) * 16;
+  unsigned char* base = Wt + (size_t)tile * (2 * FT_B_BYTES) + (size_t)rg * FT_SBO + kq * FT_LBO + (l & 7) * 16;
   *(float4*)base = hi;
-  *(float4*)(base + FT_TILE_BYTES) = lo;
+  *(float4*)(base + FT_B_BYTES) = lo;
 }
 
 // X re-tiled per K tile: Xtile[kt][i][kk] = X[kt*32 + kk, i] (zero beyond N), so that the GEMM kernel fetches
@@ -115,7 +115,7 @@ __device__ __forceinline__ void ft_mbar_wait(uint32_t mbar_a, uint32_t parity) {
 template <int TI, int TC>
 __device__ __forceinline__ void ft_epi_xtr(const float* __restrict__ xr, int DX, const float* __restrict__ Rs, int D,
                                            float* __restrict__ parts, long long Ccap, long long c0, long long C, int tid) {
-  constexpr int CB = FT_N / TC;
+  constexpr int CB = 128 / TC;  // one call covers 128 chains
   const int cb = tid % CB, ib = tid / CB;
   if (ib * TI >= D) return;
   int fi[TI];
@@ -154,13 +154,13 @@ __device__ __forceinline__ void ft_epi_xtr(const float* __restrict__ xr, int DX,
 
 // ---- the GEMM: warp-specialised, two A stages, three B slots, two TMEM accumulators -----------------------
 // Producers (warps 0-7; thread pair = pair row = TMEM lane, each thread half of the K range and half of the
-// accumulator columns), per K tile kt (32 data rows):
+// accumulator columns), per K tile kt (16 data rows):
 //   wait until the MMAs of tile kt-2 are done (A stage kt&1 and B slot (kt+1)%3 are free); thread 0 starts the
 //   bulk copy of B(kt+1); wait for the X tile (bulk-copied two tiles ahead by the issuer); build the Khatri-Rao
 //   A stage (z = x_i x_j, split into TF32 hi / lo) and ARRIVE on the stage's mbarrier -- no block-wide barrier.
 //   On the first tile of a chunk they then drain the previous chunk's TMEM accumulator into FP32 registers
 //   (two-level accumulation, see below) while the tensor core already works on the new chunk.
-// Issuer (warp 8, one lane): waits for "A built" + "B landed", issues the 12 MMAs (3xTF32 x 4 K-steps) from
+// Issuer (warp 8, one lane): waits for "A built" + "B landed", issues the 6 MMAs (3xTF32 x 2 K-steps, N = 256) from
 //   pre-built descriptors, commits to the stage's "free" mbarrier (and the accumulator's "complete" mbarrier at
 //   a chunk end), and refills the X buffer the producers just finished with.
 // QUAD = false: vec(G)[pair, chain] = sum_n Z[n, pair] w[n, chain]   (M = pairs, K = data rows; A from X tiles)
@@ -188,8 +188,8 @@ fisher_metric_tc_kernel(const FtArgs a) {
   const int PS = a.PS, ldh = a.ldh;
   extern __shared__ __align__(1024) unsigned char ft_smem[];
   unsigned char* Astage = ft_smem;                                  // 2 x [A_hi | A_lo]
-  unsigned char* Bslot = ft_smem + 2 * 2 * FT_TILE_BYTES;           // 3 x [B_hi | B_lo] (one bulk copy each)
-  float* xs0 = (float*)(ft_smem + (2 * 2 + 3 * 2) * FT_TILE_BYTES);  // 2 x [D][FT_XS] X tiles
+  unsigned char* Bslot = ft_smem + 2 * 2 * FT_A_BYTES;              // 3 x [B_hi | B_lo] (one bulk copy each)
+  float* xs0 = (float*)(ft_smem + FT_REGION);                       // 2 x [D][FT_XS] X tiles / the staged data rows
   __shared__ uint32_t tmem_base_s;
   // 0,1: A stage free (MMAs done); 2,3: A stage built; 4,5,6: B slot landed; 7,8: X tile landed; 9,10: accumulator complete
   __shared__ __align__(8) unsigned long long mbar[11];
@@ -202,7 +202,7 @@ fisher_metric_tc_kernel(const FtArgs a) {
 #pragma unroll
   for (int i = 0; i < 11; ++i) mb[i] = (uint32_t)__cvta_generic_to_shared(&mbar[i]);
   const uint32_t xbytes = (uint32_t)D * FT_XS * 4;
-  const uint32_t bbytes = 2 * FT_TILE_BYTES;
+  const uint32_t bbytes = 2 * FT_B_BYTES;
   const int ktiles = QUAD ? PS / FT_KT : (N + FT_KT - 1) / FT_KT;
   const int nchunks = (ktiles + FT_KC - 1) / FT_KC;
   const int DX = D | 1;  // QUAD: odd row stride of the staged data rows xr[128][DX] (lanes = rows: conflict-free)
@@ -252,15 +252,15 @@ fisher_metric_tc_kernel(const FtArgs a) {
       bulk(Bslot, Wt + (size_t)ct * ktiles * bbytes, bbytes, mb[4]);
       const uint64_t dA0 = ft_smem_desc((uint32_t)__cvta_generic_to_shared(Astage));
       const uint64_t dB0 = ft_smem_desc((uint32_t)__cvta_generic_to_shared(Bslot));
-      constexpr uint64_t TILE16 = FT_TILE_BYTES >> 4;  // descriptor address units are 16 bytes
+      constexpr uint64_t ATILE16 = FT_A_BYTES >> 4, BTILE16 = FT_B_BYTES >> 4;  // descriptor address units are 16 bytes
       for (int j = 0; j < ktiles; ++j) {
         const int s = j & 1, slot = j % 3;
         ft_mbar_wait(mb[2 + s], (uint32_t)((j >> 1) & 1));   // A stage built (and X buffer s no longer read)
         if (!QUAD && j + 2 < ktiles) bulk(xs0 + (size_t)s * D * FT_XS, Xtile + (size_t)(j + 2) * D * FT_XS, xbytes, mb[7 + s]);
         ft_mbar_wait(mb[4 + slot], (uint32_t)((j / 3) & 1));  // B slot landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t a_hi = dA0 + (uint64_t)s * 2 * TILE16, a_lo = a_hi + TILE16;
-        const uint64_t b_hi = dB0 + (uint64_t)slot * 2 * TILE16, b_lo = b_hi + TILE16;
+        const uint64_t a_hi = dA0 + (uint64_t)s * 2 * ATILE16, a_lo = a_hi + ATILE16;
+        const uint64_t b_hi = dB0 + (uint64_t)slot * 2 * BTILE16, b_lo = b_hi + BTILE16;
         const int chunk = j / FT_KC;
         const uint32_t td = tmem_d + (uint32_t)((chunk & 1) * FT_N);
 #pragma unroll
@@ -294,7 +294,7 @@ fisher_metric_tc_kernel(const FtArgs a) {
     }
     // Two-level accumulation.  The tensor core adds partial products into TMEM with truncation, a
     // bias that grows linearly with the number of accumulated K steps (measured: 2.3e-5 relative at
-    // N = 1000, 4.5e-5 at N = 2000).  Every FT_KC stages (128 data rows) the chunk is drained from TMEM
+    // N = 1000, 4.5e-5 at N = 2000).  Every FT_KC stages (128 K steps) the chunk is drained from TMEM
     // and added to FP32 register accumulators with round-to-nearest; the next chunk restarts at zero.
     constexpr int NH = FT_N / 2;  // accumulator columns (chains) owned by this thread
     float acc[NH];
@@ -328,8 +328,8 @@ fisher_metric_tc_kernel(const FtArgs a) {
     for (int kt = 0; kt < ktiles; ++kt) {
       const int s = kt & 1, use = kt >> 1;
       const float* xs = xs0 + (size_t)s * D * FT_XS;
-      unsigned char* A_hi = Astage + (size_t)s * 2 * FT_TILE_BYTES;
-      unsigned char* A_lo = A_hi + FT_TILE_BYTES;
+      unsigned char* A_hi = Astage + (size_t)s * 2 * FT_A_BYTES;
+      unsigned char* A_lo = A_hi + FT_A_BYTES;
       if (kt >= 2) ft_mbar_wait(mb[s], (uint32_t)((use - 1) & 1));  // MMAs of tile kt - 2 done: A stage s, B slot (kt+1)%3 free
       if (tid == 0 && kt + 1 < ktiles)
         bulk(Bslot + (size_t)((kt + 1) % 3) * bbytes, Wt + ((size_t)ct * ktiles + kt + 1) * bbytes, bbytes, mb[4 + (kt + 1) % 3]);
@@ -385,7 +385,7 @@ fisher_metric_tc_kernel(const FtArgs a) {
 
     if (QUAD && EPI == 1) {
       // every MMA has completed (the last accumulator is drained): the operand stages are free and hold R now
-      float* Rs = (float*)ft_smem;  // [128 chains][129]: conflict-free for lanes = rows (write) and lanes = chains (read)
+      float* Rs = (float*)ft_smem;  // [256 chains][129]: conflict-free for lanes = rows (write) and lanes = chains (read)
       const int n = m0 + row;
       const float yn = (n < N) ? __ldg(a.y + n) : 0.f;
 #pragma unroll
@@ -402,8 +402,12 @@ fisher_metric_tc_kernel(const FtArgs a) {
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 producer warps (the issuer warp is not involved)
       // parts[m tile][i][c] = sum_r x[r, i] R[r, c]: a 128 x D x 128 product on the FP32 pipe, register-tiled
       float* pbase = a.parts + (size_t)blockIdx.x * D * a.Ccap;
-      if (D <= 32) ft_epi_xtr<4, 4>(xs0, DX, Rs, D, pbase, a.Ccap, c0, C, tid);
-      else ft_epi_xtr<8, 8>(xs0, DX, Rs, D, pbase, a.Ccap, c0, C, tid);
+#pragma unroll 1
+      for (int h = 0; h < FT_N / 128; ++h) {  // 128 chains at a time
+        if (c0 + h * 128 >= C) break;
+        if (D <= 32) ft_epi_xtr<4, 4>(xs0, DX, Rs + h * 128 * 129, D, pbase, a.Ccap, c0 + h * 128, C, tid);
+        else ft_epi_xtr<8, 8>(xs0, DX, Rs + h * 128 * 129, D, pbase, a.Ccap, c0 + h * 128, C, tid);
+      }
     } else if (QUAD) {
       // epilogue: registers -> h[c, n] (chain-major rows of length ldh; lanes = consecutive data rows: coalesced)
       const int n = m0 + row;
@@ -465,7 +469,7 @@ quadform_b_kernel(const float* __restrict__ A, int D, int P, const short2* __res
   const long long tile = gid >> 10;
   if (tile >= ctiles * ktiles) return;
   const int l = (int)(gid & 1023);
-  const int rg = l >> 6, row = rg * 8 + (l & 7), kq = (l >> 3) & 7;
+  const int rg = l >> 5, row = rg * 8 + (l & 7), kq = (l >> 3) & 3;  // a warp = one 8-row group = 512 contiguous bytes
   const long long ct = tile / ktiles;
   if (ct * FT_N >= C) return;
   const int kt = (int)(tile - ct * ktiles);
@@ -493,9 +497,9 @@ quadform_b_kernel(const float* __restrict__ A, int D, int P, const short2* __res
   }
   float4 hi, lo;
   ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
-  unsigned char* base = Bt + (size_t)tile * (2 * FT_TILE_BYTES) + (size_t)rg * FT_SBO + kq * FT_LBO + (l & 7) * 16;
+  unsigned char* base = Bt + (size_t)tile * (2 * FT_B_BYTES) + (size_t)rg * FT_SBO + kq * FT_LBO + (l & 7) * 16;
   *(float4*)base = hi;
-  *(float4*)(base + FT_TILE_BYTES) = lo;
+  *(float4*)(base + FT_B_BYTES) = lo;
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------
@@ -563,7 +567,7 @@ int gb::fisher_metric_launch(const gb200_target_desc* t, const void* position, v
   const int N = (int)t->N, D = t->D, ldx = (int)t->params[1];
   const int ktiles = (N + FT_KT - 1) / FT_KT;
   const long long ctiles = (C + FT_N - 1) / FT_N;
-  const int64_t wt_bytes = (int64_t)ctiles * ktiles * 2 * FT_TILE_BYTES;
+  const int64_t wt_bytes = (int64_t)ctiles * ktiles * 2 * FT_B_BYTES;
   const int64_t need = wt_bytes + (int64_t)ktiles * D * FT_XS * 4;
   if (workspace_bytes < need) { set_error("fisher_metric: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)need); return GB200_ERR_INVALID_ARGUMENT; }
   if (ldx % 4 != 0 || ((uintptr_t)workspace & 15) != 0) { set_error("fisher_metric: ldx must be a multiple of 4 and the workspace 16-byte aligned"); return GB200_ERR_INVALID_ARGUMENT; }
@@ -589,7 +593,7 @@ int gb::fisher_metric_launch(const gb200_target_desc* t, const void* position, v
 static int64_t quadform_ws(int D, int64_t C, int64_t* bt_bytes, int* PS_out) {
   const int PS = ft_ps(D);
   const int64_t ctiles = (C + FT_N - 1) / FT_N;
-  const int64_t bt = ctiles * (PS / FT_KT) * 2 * FT_TILE_BYTES;
+  const int64_t bt = ctiles * (PS / FT_KT) * 2 * FT_B_BYTES;
   if (bt_bytes) *bt_bytes = bt;
   if (PS_out) *PS_out = PS;
   return bt + (int64_t)PS * sizeof(short2);
@@ -636,5 +640,5 @@ extern "C" int64_t gb200_logreg_fisher_metric_workspace(const gb200_target_desc*
   const int64_t ktiles = ((int64_t)t->N + FT_KT - 1) / FT_KT;
   const int64_t ctiles = (C + FT_N - 1) / FT_N;
   // pre-split W^T tiles (hi + lo), see fisher_weights_kernel, + the re-tiled X (fisher_xtile_kernel)
-  return ctiles * ktiles * 2 * FT_TILE_BYTES + ktiles * (int64_t)t->D * FT_XS * 4;
+  return ctiles * ktiles * 2 * FT_B_BYTES + ktiles * (int64_t)t->D * FT_XS * 4;
 }

@@ -6,14 +6,21 @@
 namespace gb {
 
 constexpr int FT_M = 128;      // pairs (metric GEMM) / data rows (quadratic-form GEMM) per CTA: MMA M
-constexpr int FT_N = 128;      // chains per CTA (MMA N)
-constexpr int FT_KT = 32;      // K extent of one stage
-constexpr int FT_KC = 4;       // stages per TMEM accumulation chunk (see the epilogue note)
-constexpr int FT_THREADS = 288;  // warps 0-7: operand producers + accumulator drainers (2 threads per pair row); warp 8: TMA / MMA issuer
+constexpr int FT_N = 256;      // chains per CTA (MMA N).  With N = 128 the MMA operand fetch alone (A 4 KB + B 4 KB per
+                               // 64-cycle tf32 MMA) saturates the 128 B/clk of shared memory and leaves nothing for the
+                               // operand producers (measured: tensor pipe 48-53 %); N = 256 needs 96 B/clk and builds
+                               // each Khatri-Rao A stage once per 256 chains instead of once per 128.
+constexpr int FT_KT = 16;      // K extent of one stage
+constexpr int FT_KC = 8;       // stages per TMEM accumulation chunk: 128 K steps (see the epilogue note)
+constexpr int FT_THREADS = 288;  // warps 0-7: operand producers + accumulator drainers (2 threads per row); warp 8: TMA / MMA issuer
 constexpr int FT_XS = FT_KT + 4;  // padded row stride (floats) of the staged X tile: conflict-free float4 row reads
 constexpr int FT_LBO = 128;                  // bytes
 constexpr int FT_SBO = (FT_KT / 4) * 128;    // bytes
-constexpr int FT_TILE_BYTES = FT_M * FT_KT * 4;
+constexpr int FT_A_BYTES = FT_M * FT_KT * 4;  // one A tile (hi or lo)
+constexpr int FT_B_BYTES = FT_N * FT_KT * 4;  // one B tile (hi or lo)
+constexpr int FT_STAGE_REGION = 2 * 2 * FT_A_BYTES + 3 * 2 * FT_B_BYTES;  // 2 A stages + 3 B slots (hi + lo each)
+constexpr int FT_EPI_REGION = FT_N * 129 * 4;                             // R[chain][129] of the fused epilogue
+constexpr int FT_REGION = ((FT_STAGE_REGION > FT_EPI_REGION ? FT_STAGE_REGION : FT_EPI_REGION) + 1023) / 1024 * 1024;
 
 // phases of a chain in the lock-step sampler (rmhmc_lockstep.cu)
 enum { LS_PH_FIRST0 = 0, LS_PH_FIRST = 1, LS_PH_ITER = 2, LS_PH_EXPL = 3, LS_PH_END = 4, LS_PH_DONE = 5 };
@@ -55,7 +62,7 @@ int ft_launch_quad_b_packed(const float* Ap, int D, long long C, const int* n_ac
                             cudaStream_t s);
 int ft_set_attributes(int D);  // cudaFuncSetAttribute for both GEMM kernels (outside stream capture)
 inline int ft_ps(int D) { const int P = D * (D + 1) / 2; return (P + FT_KT - 1) / FT_KT * FT_KT; }
-inline size_t ft_metric_smem(int D) { return 10 * (size_t)FT_TILE_BYTES + 2 * (size_t)D * FT_XS * 4 + 1024; }
-inline size_t ft_quad_smem(int D) { return 10 * (size_t)FT_TILE_BYTES + (size_t)FT_M * (D | 1) * 4 + 1024; }
+inline size_t ft_metric_smem(int D) { return (size_t)FT_REGION + 2 * (size_t)D * FT_XS * 4 + 1024; }
+inline size_t ft_quad_smem(int D) { return (size_t)FT_REGION + (size_t)FT_M * (D | 1) * 4 + 1024; }
 
 }  // namespace gb

@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(128) lmc_kernel(const TransArgs a, const Targe
         store_scalar<R>(a.out_logp, chain, lp);
         store_scalar<R>(a.out_vol, chain, J);
         if (a.opts.sample_accept != nullptr) ((R*)a.opts.sample_accept)[it * a.C + chain] = mh.p_accept;
+        if (a.opts.accept_sum != nullptr) ((R*)a.opts.accept_sum)[chain] += mh.p_accept;
         if (!LEAN && da != nullptr)
           dual_averaging_update<R>(da, mh.p_accept, (R)a.opts.da_target, (R)a.opts.da_t0, (R)a.opts.da_gamma,
                                    (R)a.opts.da_kappa);

@@ -182,18 +182,18 @@ __global__ void __launch_bounds__(1024) ls_compact_kernel(const LsBuf b, const L
 }
 
 // eta = X q, s = sigmoid(eta), w = s(1-s) for the running chains: W operand tiles of the metric GEMM (TF32 hi / lo in
-// the UMMA canonical layout, one 32 KB block per (chain tile, K tile), see fisher_weights_kernel), s[slot, n], and
-// for chains at the end of their trajectory the log-density partial sums over this thread's 16 data rows.
+// the UMMA canonical layout, one 32 KB block per (256-chain tile, 16-row K tile), see fisher_weights_kernel), s[slot, n],
+// and for chains at the end of their trajectory the log-density partial sums over the K tile's 16 data rows.
 __global__ void __launch_bounds__(256) ls_weights_kernel(const LsBuf b, const LsDims d) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long tile = gid >> 10;  // 1024 threads per (chain tile, K tile): 128 rows x 8 k-quads
+  const long long tile = gid >> 10;  // 1024 threads per (chain tile, K tile): 256 rows x 4 k-quads
   const long long nact = b.n_active[0];
   const int ktiles = d.ktF;
   if (tile >= d.ctiles * ktiles) return;
   const long long ct = tile / ktiles;
   if (ct * FT_N >= nact) return;  // warp-uniform (a warp lies inside one tile)
   const int l = (int)(gid & 1023);
-  const int rg = l >> 6, row = rg * 8 + (l & 7), kq = (l >> 3) & 7;
+  const int rg = l >> 5, row = rg * 8 + (l & 7), kq = (l >> 3) & 3;  // a warp = one 8-row group = one chain-octet
   const int kt = (int)(tile - ct * ktiles);
   const long long j = ct * FT_N + row;
   const int n = kt * FT_KT + 4 * kq;
@@ -225,15 +225,15 @@ __global__ void __launch_bounds__(256) ls_weights_kernel(const LsBuf b, const Ls
         if (n + e < N) lp += __ldg(b.y + n + e) * eta[e] - (fmaxf(eta[e], 0.f) + log1pf(expf(-fabsf(eta[e]))));  // jnp.logaddexp(0, eta)
     }
   }
-  // the four k-quads of a chain inside this warp sit at lanes (l & 7) + 8 m
+  // the four k-quads of a chain sit at lanes (l & 7) + 8 kq of this warp
   lp += __shfl_xor_sync(0xffffffffu, lp, 8);
   lp += __shfl_xor_sync(0xffffffffu, lp, 16);
-  if (end && (kq & 3) == 0) b.lp_parts[((size_t)kt * 2 + (kq >> 2)) * d.Ccap + j] = lp;
+  if (end && kq == 0) b.lp_parts[(size_t)kt * d.Ccap + j] = lp;
   float4 hi, lo;
   ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
-  unsigned char* base = b.Wt + (size_t)tile * (2 * FT_TILE_BYTES) + (size_t)rg * FT_SBO + kq * FT_LBO + (l & 7) * 16;
+  unsigned char* base = b.Wt + (size_t)tile * (2 * FT_B_BYTES) + (size_t)rg * FT_SBO + kq * FT_LBO + (l & 7) * 16;
   *(float4*)base = hi;
-  *(float4*)(base + FT_TILE_BYTES) = lo;
+  *(float4*)(base + FT_B_BYTES) = lo;
 }
 
 // ---- per-chain dense algebra: blocked Cholesky / inverse with the matrix in REGISTERS ---------------------------
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(256) ls_reduce_kernel(const LsBuf b, const LsD
     b.dHt[(size_t)i * d.Ccap + j] = s;
   } else if (b.slot_phase[j] == LS_PH_END) {
     float s = 0.f;
-    for (int k = 0; k < 2 * d.ktF; ++k) s += b.lp_parts[(size_t)k * d.Ccap + j];
+    for (int k = 0; k < d.ktF; ++k) s += b.lp_parts[(size_t)k * d.Ccap + j];
     b.lpt[j] = s;
   }
 }
@@ -660,6 +660,7 @@ __global__ void __launch_bounds__(256) ls_advance_kernel(const LsBuf b, const Ls
       store_scalar<float>(a.info.accept_uniform, c, mh.u);
       if (a.info.fp_iters) a.info.fp_iters[c] = b.iters[c];
       if (a.opts.sample_accept != nullptr) ((float*)a.opts.sample_accept)[tr * a.C + c] = mh.p_accept;
+      if (a.opts.accept_sum != nullptr) ((float*)a.opts.accept_sum)[c] += mh.p_accept;
       if (a.opts.dual_averaging != nullptr)
         dual_averaging_update<float>((float*)a.opts.dual_averaging + (size_t)c * 5, mh.p_accept, (float)a.opts.da_target,
                                      (float)a.opts.da_t0, (float)a.opts.da_gamma, (float)a.opts.da_kappa);
@@ -821,10 +822,10 @@ int64_t ls_carve(const LsDims& d, unsigned char* base, LsBuf* b) {
   t.sbuf = (float*)take(C * (int64_t)d.ldn * 4);
   t.Gp = (float*)take(C * (int64_t)d.P * 4); t.Ap = (float*)take(C * (int64_t)d.P * 4);
   t.parts = (float*)take((int64_t)d.mtQ * D * C * 4);
-  t.lp_parts = (float*)take(2 * (int64_t)d.ktF * C * 4);
+  t.lp_parts = (float*)take((int64_t)d.ktF * C * 4);
   t.dHt = (float*)take(D * C * 4); t.lpt = (float*)take(C * 4);
-  t.Wt = (unsigned char*)take(d.ctiles * d.ktF * 2 * (int64_t)FT_TILE_BYTES);
-  t.Bt = (unsigned char*)take(d.ctiles * d.ktQ * 2 * (int64_t)FT_TILE_BYTES);
+  t.Wt = (unsigned char*)take(d.ctiles * d.ktF * 2 * (int64_t)FT_B_BYTES);
+  t.Bt = (unsigned char*)take(d.ctiles * d.ktQ * 2 * (int64_t)FT_B_BYTES);
   t.Xtile = (float*)take((int64_t)d.ktF * D * FT_XS * 4);
   t.pairs = (short2*)take((int64_t)d.PS * sizeof(short2));
   if (b) *b = t;

@@ -524,6 +524,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1) rmhmc_logreg_big_kernel(const T
         store_scalar<float>(a.info.accept_uniform, chain, mh.u);
         if (a.info.fp_iters) a.info.fp_iters[chain] = iters_total;
         if (a.opts.sample_accept != nullptr) ((float*)a.opts.sample_accept)[it * a.C + chain] = mh.p_accept;
+        if (a.opts.accept_sum != nullptr) ((float*)a.opts.accept_sum)[chain] += mh.p_accept;
         if (da != nullptr)
           dual_averaging_update<float>(da, mh.p_accept, (float)a.opts.da_target, (float)a.opts.da_t0,
                                        (float)a.opts.da_gamma, (float)a.opts.da_kappa);

@@ -109,6 +109,12 @@ def _check_position(position, target):
     return position.contiguous()
 
 
+def _check_field(name, t, shape, ref):
+    if not isinstance(t, torch.Tensor) or tuple(t.shape) != tuple(shape) or t.dtype != ref.dtype or t.device != ref.device:
+        got = (tuple(t.shape), t.dtype, t.device) if isinstance(t, torch.Tensor) else type(t).__name__
+        raise ValueError(f"{name} must be a {ref.dtype} tensor of shape {tuple(shape)} on {ref.device}; got {got}")
+
+
 def _init(position, logdensity_fn, with_volume: bool):
     target = as_target(logdensity_fn)
     q = _check_position(position, target)
@@ -198,6 +204,19 @@ class _Engine:
         C_, D = q.shape
         dev, dt = q.device, q.dtype
         fields = [q] + [t.contiguous() for t in state[1:] if t is not None]  # rmhmc carries no volume_adjustment
+        want = 4 if self.with_volume else 3
+        if len(fields) < want:
+            raise ValueError(f"state needs {want} fields (position, logdensity, logdensity_grad"
+                             + (", volume_adjustment)" if self.with_volume else ")"))
+        for name, t, shape in zip(("position", "logdensity", "logdensity_grad", "volume_adjustment"), fields[:want],
+                                  ((C_, D), (C_,), (C_, D), (C_,))):
+            _check_field(name, t, shape, q)
+        if out_state is not None:
+            for name, t, shape in zip(("position", "logdensity", "logdensity_grad", "volume_adjustment"),
+                                      [t for t in out_state if t is not None][:want], ((C_, D), (C_,), (C_, D), (C_,))):
+                _check_field("out_state." + name, t, shape, q)
+                if not t.is_contiguous():
+                    raise ValueError(f"out_state.{name} must be contiguous")
         if out_state is None:
             out = [torch.empty_like(t) for t in fields]
         else:
@@ -287,12 +306,15 @@ class _StepFn:
 
 def run_fused(step_fn, rng_key, state, num_samples: int, *, first: int = 0, total: Optional[int] = None,
               chain_offset: int = 0, total_chains: Optional[int] = None, return_samples: bool = False,
-              return_accept: bool = False, dual_averaging=None, da_target: float = 0.8, inplace: bool = False):
+              return_accept=False, dual_averaging=None, da_target: float = 0.8, inplace: bool = False,
+              out_samples=None, out_accept=None):
     """Run ``num_samples`` transitions in ONE launch with in-kernel key derivation
     ``split(split(rng_key, total)[t], total_chains)[chain_offset + c]`` -- the driver loop of
     examples/funnel/main.py:7-25 (``inference_loop_multiple_chains``) without the host round trip.
     Identical, bit for bit, to calling ``step`` ``num_samples`` times with those keys.
-    Returns (state, samples[T, C, D] | None, acceptance_rate[T, C] | None)."""
+    Returns (state, samples[T, C, D] | None, acceptance_rate[T, C] | None); with ``return_accept="mean"`` the third
+    item is the per-chain mean acceptance rate [C], accumulated inside the kernels (no [T, C] buffer).
+    ``out_samples`` / ``out_accept``: caller-owned result buffers (allocation stays outside a timed region)."""
     eng = step_fn.engine if isinstance(step_fn, _StepFn) else step_fn
     q = state[0]
     C_, D = q.shape
@@ -305,17 +327,31 @@ def run_fused(step_fn, rng_key, state, num_samples: int, *, first: int = 0, tota
     ks.chain_offset, ks.total_chains = chain_offset, total_chains
     opts = N.RunOpts()
     samples = acc = None
-    if return_samples:
-        samples = torch.empty((num_samples, C_, D), dtype=q.dtype, device=q.device)
+    if return_samples or out_samples is not None:
+        samples = _result_buffer(out_samples, (num_samples, C_, D), q)
         opts.samples = N.ptr(samples)
-    if return_accept:
-        acc = torch.empty((num_samples, C_), dtype=q.dtype, device=q.device)
+    if return_accept == "mean":
+        acc = _result_buffer(out_accept, (C_,), q)
+        acc.zero_()
+        opts.accept_sum = N.ptr(acc)
+    elif return_accept or out_accept is not None:
+        acc = _result_buffer(out_accept, (num_samples, C_), q)
         opts.sample_accept = N.ptr(acc)
     if dual_averaging is not None:
         opts.dual_averaging = N.ptr(dual_averaging)
         opts.da_target, opts.da_t0, opts.da_gamma, opts.da_kappa = da_target, 10.0, 0.05, 0.75
     out, _ = eng.launch(state, ks, want_info=False, opts=opts, out_state=list(state) if inplace else None)
+    if return_accept == "mean":
+        acc.mul_(1.0 / num_samples)
     return eng.make_state(out), samples, acc
+
+
+def _result_buffer(buf, shape, like):
+    if buf is None:
+        return torch.empty(shape, dtype=like.dtype, device=like.device)
+    if tuple(buf.shape) != tuple(shape) or buf.dtype != like.dtype or buf.device != like.device or not buf.is_contiguous():
+        raise ValueError(f"result buffer must be a contiguous {like.dtype} tensor of shape {tuple(shape)} on {like.device}")
+    return buf
 
 
 # ------------------------------------------------------------------------------------ façades

@@ -150,8 +150,9 @@ typedef struct gb200_run_opts {
   void* sample_accept;         /* [num_transitions, C] acceptance_rate per transition */
   const void* noise_override;  /* [C, D] use this z instead of drawing (test surface, num_transitions==1) */
   const void* uniform_override;/* [C] use this accept uniform (test surface, num_transitions==1) */
-  void* dual_averaging;        /* [C, 5] (log_x, log_x_avg, step, avg_error, mu): fused per-chain dual averaging
-                                  (optimizers/dual_averaging.py:101-123); step size = exp(log_x) */
+  void* dual_averaging;        /* [C, 5] (log_x, log_x_avg, step, avg_error, mu) IN THE STATE DTYPE: fused per-chain dual
+                                  averaging (optimizers/dual_averaging.py:101-123); step size = exp(log_x).  samples,
+                                  sample_accept and accept_sum are in the state dtype as well. */
   double da_target;            /* target acceptance rate (adaptation/step_size_adaptation.py:103) */
   double da_t0, da_gamma, da_kappa; /* (10, 0.05, 0.75) */
   void* workspace;             /* optional device scratch (>= 16 bytes): dynamic chain hand-out of the CTA-per-chain
@@ -159,6 +160,8 @@ typedef struct gb200_run_opts {
   int64_t workspace_bytes;
   void* plan;                  /* gb200_plan* (below): rmhmc on the logistic-regression target runs the lock-step
                                   tcgen05 sampler */
+  void* accept_sum;            /* [C] running sum: += acceptance_rate of every transition of the launch (caller zeroes);
+                                  the per-chain mean acceptance of a fused run without a [T, C] buffer */
 } gb200_run_opts;
 
 int gb200_version(void);

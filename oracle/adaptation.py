@@ -40,3 +40,33 @@ def step_size_adaptation(step_fn, init_state, keys_fn, num_steps, num_chains,
         eps = np.exp(st["log_x"]).astype(dtype)
     final = np.maximum(np.exp(st["log_x_avg"]), dtype(lower_bound)).astype(dtype)
     return state, final, st
+
+
+def build_schedule(num_steps, initial_buffer_size=75, final_buffer_size=50, first_window_size=25):
+    """adaptation/window_adaptation.py:360-450 restated statement by statement (the specification the product's
+    arithmetic formulation in geomjax_b200/adaptation.py is compared with)."""
+    schedule = []
+    if num_steps < 20:
+        schedule += [(0, False)] * num_steps
+    else:
+        if initial_buffer_size + first_window_size + final_buffer_size > num_steps:
+            initial_buffer_size = int(0.15 * num_steps)
+            final_buffer_size = int(0.1 * num_steps)
+            first_window_size = num_steps - initial_buffer_size - final_buffer_size
+        schedule += [(0, False)] * (initial_buffer_size - 1)
+        schedule.append((0, False))
+        final_buffer_start = num_steps - final_buffer_size
+        next_window_size = first_window_size
+        next_window_start = initial_buffer_size
+        while next_window_start < final_buffer_start:
+            current_start, current_size = next_window_start, next_window_size
+            if 3 * current_size <= final_buffer_start - current_start:
+                next_window_size = 2 * current_size
+            else:
+                current_size = final_buffer_start - current_start
+            next_window_start = current_start + current_size
+            schedule += [(1, False)] * (next_window_start - 1 - current_start)
+            schedule.append((1, True))
+        schedule += [(0, False)] * (num_steps - 1 - final_buffer_start)
+        schedule.append((0, False))
+    return schedule

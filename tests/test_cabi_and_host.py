@@ -111,6 +111,12 @@ def test_build_schedule_matches_reference_shape():
     assert build_schedule(10) == [(0, False)] * 10
     s = build_schedule(100)
     assert len(s) == 100 and [i for i, (_, e) in enumerate(s) if e] == [89]
+    # element by element against the oracle's statement-by-statement restatement of the reference
+    from oracle.adaptation import build_schedule as ref
+    for n in list(range(0, 260)) + [300, 500, 999, 1000, 1001, 2500, 10000]:
+        assert build_schedule(n) == ref(n), n
+    for args in [(400, 100, 40, 10), (1000, 10, 10, 5), (150, 75, 50, 25), (2000, 200, 100, 50)]:
+        assert build_schedule(*args) == ref(*args), args
 
 
 def test_bench_reference_arm_contract():
