@@ -47,6 +47,17 @@ CASES = {
     "rmhmc_softabs_funnel_d2": ("rmhmc", "softabs", 2, 16, 4, 0.05, {}),
 }
 
+# The exact shapes BASELINE.json names (bench/configs.json: init position, step size, L, data seed 0) with the bench's
+# key tree split(split(PRNGKey(0), T)[0], C)[c]; written to baseline_shapes.npz.
+BASELINE_CASES = {
+    "c1_lmc_funnel_d2_as_shipped": ("lmc", "funnel", 2, 8, 8, 0.1, {"init": "ones", "total_transitions": 1000}),
+    "c2_lmcmonge_funnel_d20": ("lmcmonge", "funnel", 20, 64, 8, 0.001016, {"half_step": "omega", "init": "ones"}),
+    "c2_lmcmonge_fixed_funnel_d20": ("lmcmonge", "funnel", 20, 64, 8, 0.3509, {"half_step": "omega_fixed", "init": "ones"}),
+    "c3_lmc_funnel_d100": ("lmc", "funnel", 100, 8, 8, 0.05, {"init": "ones"}),
+    "c4_rmhmc_logreg_d25_n1000": ("rmhmc", "logreg", 25, 16, 6, 0.1, {"N": 1000, "init": "zeros"}),
+}
+CASES.update(BASELINE_CASES)
+
 
 def make_target(kind, D, extra):
     if kind == "funnel":
@@ -55,11 +66,17 @@ def make_target(kind, D, extra):
         return T.softabs_metric(T.NealFunnel(D), alpha=1e6)
     if kind == "logreg":
         X, y = T.make_logreg_data(extra["N"], D, 0)
-        return T.LogisticRegression(X, y, 0.01)
+        tgt = T.LogisticRegression(X, y, 0.01)
+        # the same contractions re-associated so that dG (C, D, D, D) is never materialised (minutes otherwise)
+        tgt.structured_dmetric = extra["N"] * D ** 3 > 1e7
+        return tgt
     raise ValueError(kind)
 
 
-def make_inputs(kind, D, C, seed):
+def make_inputs(kind, D, C, seed, extra=None):
+    if extra and "init" in extra:
+        q = (np.ones if extra["init"] == "ones" else np.zeros)((C, D), np.float32)
+        return q, S.chain_keys(P.key(0), extra.get("total_transitions", 1 << 20), 0, C)
     rng = np.random.default_rng(seed)
     if kind == "logreg":
         q = (0.3 * rng.standard_normal((C, D))).astype(np.float32)
@@ -76,7 +93,7 @@ def make_inputs(kind, D, C, seed):
 def run_case(name):
     sampler, kind, D, C, L, eps, extra = CASES[name]
     tgt = make_target(kind, D, extra)
-    q, keys = make_inputs(kind, D, C, seed=sum(map(ord, name)))
+    q, keys = make_inputs(kind, D, C, seed=sum(map(ord, name)), extra=extra)
     if sampler == "rmhmc":
         st, info = S.rmhmc_step(keys, S.rmhmc_init(q, tgt), tgt, eps, L)
     elif sampler == "lmc":
@@ -99,19 +116,22 @@ def run_case(name):
 
 
 def main():
-    flat = {}
-    for name in CASES:
-        if CASES[name][1] == "softabs" and not hasattr(T, "softabs_metric"):
-            continue
-        for k, v in run_case(name).items():
-            flat[f"{name}/{k}"] = np.asarray(v)
     try:
         rev = subprocess.run(["git", "-C", ROOT, "rev-parse", "HEAD"], capture_output=True, text=True).stdout.strip()
     except Exception:
         rev = "unknown"
-    flat["_meta/oracle_git_rev"] = np.array(rev)
-    np.savez_compressed(os.path.join(HERE, "static_kernels.npz"), **flat)
-    print(f"wrote static_kernels.npz: {len(flat)} arrays, oracle rev {rev}")
+    only_baseline = "--baseline-only" in sys.argv
+    for fname, names in (("static_kernels.npz", [n for n in CASES if n not in BASELINE_CASES]),
+                         ("baseline_shapes.npz", list(BASELINE_CASES))):
+        if only_baseline and fname != "baseline_shapes.npz":
+            continue
+        flat = {}
+        for name in names:
+            for k, v in run_case(name).items():
+                flat[f"{name}/{k}"] = np.asarray(v)
+        flat["_meta/oracle_git_rev"] = np.array(rev)
+        np.savez_compressed(os.path.join(HERE, fname), **flat)
+        print(f"wrote {fname}: {len(flat)} arrays, oracle rev {rev}")
 
 
 if __name__ == "__main__":

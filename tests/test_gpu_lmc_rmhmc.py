@@ -66,7 +66,9 @@ def test_lmc_vs_oracle(cuda, D, lpc, C, L, rtol):
     _close(info.energy[tm], oinfo.energy[tame], rtol=rtol, atol=2e-4, what="energy")
     _close(info.acceptance_rate[tm], oinfo.acceptance_rate[tame], rtol=10 * rtol, atol=1e-3)
     got_acc = info.is_accepted.cpu().numpy()
-    clear = np.abs(oinfo.extra["u"] - oinfo.acceptance_rate) > 4e-3
+    dp = np.abs(info.acceptance_rate.cpu().numpy() - oinfo.acceptance_rate)[tame].max()
+    clear = np.abs(oinfo.extra["u"] - oinfo.acceptance_rate) > 4 * dp + 1e-6  # 4x the observed |delta p_accept|
+    assert clear.mean() > 0.95, dp
     np.testing.assert_array_equal(got_acc[clear], oinfo.is_accepted[clear])
     same = (got_acc == oinfo.is_accepted) & tame
     _close(new.position[_t(same, cuda)], onew.position[same], rtol=rtol)
@@ -101,7 +103,9 @@ def test_rmhmc_vs_oracle(cuda, D, lpc, C, L, rtol):
     _close(ps.logdensity[tm], oinfo.proposal["logdensity"][tame], rtol=rtol, atol=2e-4)
     _close(info.energy[tm], oinfo.energy[tame], rtol=rtol, atol=3e-4, what="energy")
     got_acc = info.is_accepted.cpu().numpy()
-    clear = np.abs(oinfo.extra["u"] - oinfo.acceptance_rate) > 4e-3
+    dp = np.abs(info.acceptance_rate.cpu().numpy() - oinfo.acceptance_rate)[tame].max()
+    clear = np.abs(oinfo.extra["u"] - oinfo.acceptance_rate) > 4 * dp + 1e-6  # 4x the observed |delta p_accept|
+    assert clear[tame].mean() > 0.95, dp
     np.testing.assert_array_equal(got_acc[clear & tame], oinfo.is_accepted[clear & tame])
 
 

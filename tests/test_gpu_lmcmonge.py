@@ -68,7 +68,10 @@ def test_init_and_transition_vs_oracle(cuda, D, lpc, L, rtol):
     _close(info.acceptance_rate[tm], oinfo.acceptance_rate[tame], rtol=10 * rtol, atol=5e-4)
     # accept decisions: identical except where |u - p| is at rounding level
     got_acc = info.is_accepted.cpu().numpy()
-    clear = np.abs(oinfo.extra["u"] - oinfo.acceptance_rate) > 2e-3
+    # window = 4x the largest observed |p_accept(GPU) - p_accept(oracle)|, not a fixed constant
+    dp = np.abs(info.acceptance_rate.cpu().numpy() - oinfo.acceptance_rate)[tame].max()
+    clear = np.abs(oinfo.extra["u"] - oinfo.acceptance_rate) > 4 * dp + 1e-6
+    assert clear.mean() > 0.97, dp
     np.testing.assert_array_equal(got_acc[clear], oinfo.is_accepted[clear])
     np.testing.assert_array_equal(info.is_divergent.cpu().numpy()[~tame | clear], oinfo.is_divergent[~tame | clear])
     same = (got_acc == oinfo.is_accepted) & tame

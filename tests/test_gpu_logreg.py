@@ -45,9 +45,23 @@ def test_rmhmc_logreg_vs_oracle(cuda, Nrows, D, C, L, path):
     st = alg.init(_t(q, cuda))
     _close(st.logdensity, ost.logdensity, 1e-5, 1e-3, "init logdensity")
     _close(st.logdensity_grad, ost.logdensity_grad, 1e-4, 1e-3, "init grad")
-    new, info = alg.step(_t(keys, cuda), st)
-    ok = oinfo.extra["fp_iters"] < 50 * L  # chains whose float32 fixed point stalls at tol=1e-6 are noise-level
-    assert oinfo.is_accepted.mean() > 0.5 and ok.mean() > 0.8
+    eng = alg.step.engine
+    ks = g._native.KeySource()
+    kt = _t(keys, cuda)
+    ks.keys, ks.num_transitions = g._native.ptr(kt), 1
+    out, inf = eng.launch(st, ks, want_info=True, extra_info=True)
+    new, info = eng.make_state(out), eng.make_info(inf)
+    fp = inf["fp_iters"].cpu().numpy()
+    # chains whose float32 fixed point stalls at tol = 1e-6 (noise level of |p| ~ sqrt(N)) iterate until they hit the
+    # tolerance by chance: their end point is only defined to ~1e-4.  They are reported, not dropped: the GPU must
+    # find them slow as well and still land on the same proposal to that looser tolerance.
+    ok = oinfo.extra["fp_iters"] < 50 * L
+    assert oinfo.is_accepted.mean() > 0.5 and ok.mean() > 0.7
+    slow = ~ok
+    if slow.any():
+        assert np.median(fp[slow]) >= 10 * L, (fp[slow], oinfo.extra["fp_iters"][slow])
+        _close(info.proposal.state.position[_t(slow, cuda)], oinfo.proposal["position"][slow], 2e-3, 2e-4, "stalled chains")
+    assert abs(fp[ok].mean() - oinfo.extra["fp_iters"][ok].mean()) <= 0.25 * oinfo.extra["fp_iters"][ok].mean() + 1
     okt = _t(ok, cuda)
     scale = float(np.abs(oinfo.momentum).max())
     _close(info.momentum, oinfo.momentum, 1e-5, 3e-5 * scale, "momentum draw")
@@ -58,11 +72,51 @@ def test_rmhmc_logreg_vs_oracle(cuda, Nrows, D, C, L, path):
     _close(ps.logdensity[okt], oinfo.proposal["logdensity"][ok], 1e-5, 2e-3, "logdensity")
     _close(info.energy[okt], oinfo.energy[ok], 1e-5, 3e-3, "energy")
     _close(info.acceptance_rate[okt], oinfo.acceptance_rate[ok], 1e-2, 5e-3, "acceptance")
+    # accept decisions: identical wherever the uniform is further from the acceptance probability than 4x the
+    # largest observed |p_accept(GPU) - p_accept(oracle)| (same uniforms: the accept stream is bit-exact)
+    _close(inf["accept_uniform"], oinfo.extra["u"], 0, 0, "accept uniforms")
     got_acc = info.is_accepted.cpu().numpy()
-    clear = np.abs(oinfo.extra["u"] - oinfo.acceptance_rate) > 2e-2
+    dp = np.abs(info.acceptance_rate.cpu().numpy() - oinfo.acceptance_rate)[ok].max()
+    clear = np.abs(oinfo.extra["u"] - oinfo.acceptance_rate) > 4 * dp + 1e-6
+    assert clear[ok].mean() > 0.9, dp
     np.testing.assert_array_equal(got_acc[clear & ok], oinfo.is_accepted[clear & ok])
     same = (got_acc == oinfo.is_accepted) & ok
     _close(new.position[_t(same, cuda)], onew.position[same], 1e-4, 1e-5)
+
+
+@pytest.mark.parametrize("Nrows,D,C", [(200, 8, 40), (1000, 25, 130), (10000, 100, 6)])
+def test_logreg_midpoint_map_closer_to_float64(cuda, Nrows, D, C):
+    """North-star tolerance for a single integrator map evaluation (rel 1e-5, float32) in the form that does not
+    depend on the float32 oracle's own round-off: |CUDA - float64 oracle| <= max(2 |float32 oracle - float64 oracle|,
+    1e-5), norm-wise per chain, for every output of the implicit-midpoint map (rmhmc/integrators.py:119-142)."""
+    import geomjax_b200 as g
+    X, y = T.make_logreg_data(Nrows, D, seed=5)
+    t32 = T.LogisticRegression(X, y, 0.01)
+    t64 = T.LogisticRegression(X.astype(np.float64), y.astype(np.float64), 0.01, dtype=np.float64)
+    t32.structured_dmetric = t64.structured_dmetric = Nrows * D ** 3 > 1e9
+    rng = np.random.default_rng(D)
+    q = (0.2 * rng.standard_normal((C, D))).astype(np.float32)
+    p = (np.sqrt(Nrows) * 0.3 * rng.standard_normal((C, D))).astype(np.float32)
+    he = 0.05
+    want, o32 = {}, {}
+    for tgt, dst, dt in ((t64, want, np.float64), (t32, o32, np.float32)):
+        dT, v = S._rmhmc_kinetic_grad(tgt, q.astype(dt), p.astype(dt))
+        gr = tgt.grad(q.astype(dt))
+        dst.update(velocity=v, dHdq=dT - gr, q=q.astype(dt) + dt(he) * v, p=p.astype(dt) - dt(he) * (dT - gr),
+                   logdet=np.linalg.slogdet(tgt.metric(q.astype(dt)))[1])
+    target = g.logistic_regression(_t(X, cuda), _t(y, cuda), 0.01)
+    out = g.LockstepPlan(target, C, cuda).evaluate(0, _t(q, cuda), _t(p, cuda), half_step=he)
+    report = {}
+    for k in ("velocity", "dHdq", "q", "p"):
+        sc = np.abs(want[k]).max(axis=1, keepdims=True)
+        e_gpu = (np.abs(out[k].cpu().numpy().astype(np.float64) - want[k]) / sc).max()
+        e_o32 = (np.abs(o32[k].astype(np.float64) - want[k]) / sc).max()
+        report[k] = (e_gpu, e_o32)
+    e_gpu = np.abs(out["logdet"].cpu().numpy() - want["logdet"]).max() / np.abs(want["logdet"]).max()
+    e_o32 = np.abs(o32["logdet"] - want["logdet"]).max() / np.abs(want["logdet"]).max()
+    report["logdet"] = (e_gpu, e_o32)
+    for k, (eg, eo) in report.items():
+        assert eg <= max(2.0 * eo, 1e-5), report
 
 
 def test_logreg_fused_equals_stepwise_and_limits(cuda):
