@@ -13,6 +13,7 @@ from .samplers import (LMCInfo, LMCState, Proposal, RMHMCInfo, RMHMCState, lmc, 
 from .plan import LockstepPlan  # noqa: F401
 from .diagnostics import effective_sample_size as ess  # noqa: F401
 from .diagnostics import potential_scale_reduction as rhat  # noqa: F401
+from .diagnostics import StreamingDiagnostics, sample_streaming  # noqa: F401
 from .targets import TargetDescriptor, banana, gaussian, logistic_regression, neal_funnel, softabs  # noqa: F401
 
 __version__ = "0.1.0"

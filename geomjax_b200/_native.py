@@ -104,6 +104,9 @@ PROTOTYPES = {
     "gb200_plan_loop_mode": (C.c_char_p, [vp]),
     "gb200_plan_stats": (C.c_int, [vp, _P(_i64), _P(_i64), vp]),
     "gb200_logreg_lockstep_eval": (C.c_int, [vp, _i32, vp, vp, vp, vp, _dbl, vp, vp, vp, vp, vp, vp, vp, vp, _i64, vp]),
+    "gb200_stream_diag_workspace": (_i64, [_i64, _i32, _i32]),
+    "gb200_stream_diag_update": (C.c_int, [vp, vp, _i64, _i64, _i32, _i32, _i64, _i32, vp]),
+    "gb200_stream_diag_partial": (C.c_int, [vp, _i64, _i64, _i32, _i32, _i32, vp, vp, vp]),
     "gb200_fp32_peak_kernel": (C.c_int, [vp, _i32, _i32, _i64, vp]),
     "gb200_flops_per_chain_step": (_dbl, [_i32, _P(TargetDesc)]),
     "gb200_flops_per_transition": (_dbl, [_i32, _P(TargetDesc)]),

@@ -109,6 +109,172 @@ __global__ void __launch_bounds__(256) k_ess_partial(const R* __restrict__ x, lo
   }
 }
 
+
+// ---- streaming R-hat / ESS: the same sufficient statistics without the (T, C, D) sample tensor ---------------
+// Samples arrive in blocks [Tb, C, D] (the sample buffer of one fused launch, reused).  Per series (chain, dim) the
+// accumulator keeps the shift x0 (its first sample), S = sum y, Q = sum y^2 (y = x - x0, float64), the first K and
+// the last K shifted samples; per (lag, dim) it keeps the chain-summed raw lagged products P_k = sum_c sum_t
+// y_t y_{t+k} (float64).  diagnostics.py:122-131 centres every series on ITS OWN mean m_c, which is only known at
+// the end; with A = sum_{t < T-k} y_t = S - (sum of the last k), B = sum_{t >= k} y_t = S - (sum of the first k):
+//     sum_t (y_t - m)(y_{t+k} - m) = P_k - m (A + B) + (T - k) m^2,
+// so the correction needs only S, the head and the tail of each chain (k_stream_partial).
+struct StreamWs {
+  float* x0;      // [C, D]
+  double* S;      // [C, D]
+  double* Q;      // [C, D]
+  float* head;    // [K, C, D]
+  float* ring;    // [K, C, D] last K shifted samples, chronological
+  double* P;      // [K, D]
+};
+
+__host__ __device__ inline long long stream_align(long long x) { return (x + 255) / 256 * 256; }
+
+inline long long stream_carve(unsigned char* base, long long C, int D, int K, StreamWs* w) {
+  long long off = 0;
+  const long long CD = C * D;
+  auto take = [&](long long bytes) { unsigned char* p = base ? base + off : nullptr; off += stream_align(bytes); return p; };
+  StreamWs t;
+  t.x0 = (float*)take(CD * 4);
+  t.S = (double*)take(CD * 8);
+  t.Q = (double*)take(CD * 8);
+  t.head = (float*)take((long long)K * CD * 4);
+  t.ring = (float*)take((long long)K * CD * 4);
+  t.P = (double*)take((long long)K * D * 8);
+  if (w) *w = t;
+  return off;
+}
+
+// one block = one dimension d and up to 32 chains; shared memory holds [ring tail (K) | block (Tb) | zero pad] per
+// series with an odd stride (same conflict-free lane = series mapping as k_ess_partial)
+template <typename R>
+__global__ void __launch_bounds__(256) k_stream_update(const R* __restrict__ x, long long Tb, long long C, int D, int K,
+                                                       long long T_prev, int TS, StreamWs w) {
+  extern __shared__ float xs[];  // 32 * TS
+  const int d = blockIdx.y;
+  const long long c0 = (long long)blockIdx.x * 32;
+  const int ns = (int)min(32LL, C - c0);
+  const long long CD = C * D;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarp = blockDim.x / 32;
+  for (long long i = threadIdx.x; i < 32LL * TS; i += blockDim.x) xs[i] = 0.f;
+  __syncthreads();
+  // shifts: the first sample of the series
+  for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+    const long long sd = (c0 + s) * D + d;
+    if (T_prev == 0) w.x0[sd] = (float)x[sd];
+  }
+  __syncthreads();
+  for (long long i = threadIdx.x; i < (long long)ns * K; i += blockDim.x) {
+    const int s = (int)(i % ns);
+    const long long k = i / ns;
+    xs[(long long)s * TS + k] = T_prev == 0 ? 0.f : w.ring[k * CD + (c0 + s) * D + d];
+  }
+  for (long long i = threadIdx.x; i < (long long)ns * Tb; i += blockDim.x) {
+    const int s = (int)(i % ns);
+    const long long t = i / ns;
+    const long long sd = (c0 + s) * D + d;
+    const float y = (float)((double)x[t * CD + sd] - (double)w.x0[sd]);
+    xs[(long long)s * TS + K + t] = y;
+    if (T_prev + t < K) w.head[(T_prev + t) * CD + sd] = y;
+  }
+  __syncthreads();
+  // S, Q (float64), warp per series
+  for (int s = warp; s < ns; s += nwarp) {
+    double s1 = 0.0, s2 = 0.0;
+    for (long long t = lane; t < Tb; t += 32) {
+      const double y = (double)xs[(long long)s * TS + K + t];
+      s1 += y;
+      s2 += y * y;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+      const long long sd = (c0 + s) * D + d;
+      w.S[sd] = (T_prev == 0 ? 0.0 : w.S[sd]) + s1;
+      w.Q[sd] = (T_prev == 0 ? 0.0 : w.Q[sd]) + s2;
+    }
+  }
+  // lagged products with the newer factor inside this block: sum_u y_u y_{u - l}, u in [K, K + Tb)
+  const bool live = lane < ns;
+  const float* p = xs + (long long)(live ? lane : 0) * TS;
+  for (int l0 = 8 * warp; l0 < K; l0 += 8 * nwarp) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (long long u = K; u < K + Tb; u += 8) {
+      float a[8], bb[15];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = p[u + i];
+#pragma unroll
+      for (int i = 0; i < 15; ++i) bb[i] = p[u - l0 - 7 + i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j] = fmaf(a[i], bb[i - j + 7], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double tot = live ? (double)acc[j] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (lane == 0 && l0 + j < K) atomicAdd(&w.P[(long long)(l0 + j) * D + d], tot);
+    }
+  }
+  __syncthreads();
+  // the last K samples become the tail of the next block
+  for (long long i = threadIdx.x; i < (long long)ns * K; i += blockDim.x) {
+    const int s = (int)(i % ns);
+    const long long k = i / ns;
+    w.ring[k * CD + (c0 + s) * D + d] = xs[(long long)s * TS + Tb + k];
+  }
+}
+
+// chain-summed statistics in the layouts of k_rhat_partial (stats[3 D + 1]) and k_ess_partial (acov[num_lags, D]);
+// block = one dimension d x 256 chains
+__global__ void __launch_bounds__(256) k_stream_partial(long long T, long long C, int D, int K, int num_lags, StreamWs w,
+                                                        double* stats, double* acov) {
+  __shared__ double red[8];
+  const int d = blockIdx.y, lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+  const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+  const bool live = c < C;
+  const long long CD = C * D, sd = (live ? c : 0) * D + d;
+  const double Td = (double)T;
+  const double S = live ? w.S[sd] : 0.0, Q = live ? w.Q[sd] : 0.0;
+  const double m = S / Td;
+  auto block_sum = [&](double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+  };
+  {
+    const double mean = m + (live ? (double)w.x0[sd] : 0.0);
+    const double var = (Q - Td * m * m) / (Td - 1.0);
+    const double a = block_sum(live ? mean : 0.0), b = block_sum(live ? mean * mean : 0.0), v = block_sum(live ? var : 0.0);
+    if (threadIdx.x == 0) {
+      atomicAdd(&stats[d], a);
+      atomicAdd(&stats[D + d], b);
+      atomicAdd(&stats[2 * D + d], v);
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&stats[3 * D], (double)C);
+  if (acov == nullptr) return;
+  double headsum = 0.0, tailsum = 0.0;
+  for (int k = 0; k < num_lags; ++k) {
+    // head_k = first k samples, tail_k = last k samples
+    const double corr = live ? (-m * (2.0 * S - tailsum - headsum) + (Td - (double)k) * m * m) : 0.0;
+    const double tot = block_sum(corr);
+    if (threadIdx.x == 0) atomicAdd(&acov[(long long)k * D + d], (tot + (blockIdx.x == 0 ? w.P[(long long)k * D + d] : 0.0)) / Td);
+    if (live && k < K) {
+      headsum += (double)w.head[(long long)k * CD + sd];
+      tailsum += (double)w.ring[(long long)(K - 1 - k) * CD + sd];
+    }
+  }
+}
+
 }  // namespace gb
 
 using namespace gb;
@@ -170,6 +336,62 @@ int gb200_ess_partial(const void* samples, int64_t T, int64_t C, int32_t D, int3
     if (e == cudaSuccess) k_ess_partial<double><<<grid, block, sh, s>>>((const double*)samples, T, C, D, num_lags, (int)S, (int)TS, acov);
   }
   if (e != cudaSuccess) { set_error("ess_partial: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+
+
+// ---- streaming diagnostics (see StreamWs): N2 of SURVEY 8(f) ---------------------------------------------------
+int64_t gb200_stream_diag_workspace(int64_t C, int32_t D, int32_t max_lags) {
+  if (C < 1 || D < 1 || max_lags < 8) return -1;
+  return stream_carve(nullptr, C, D, (max_lags + 7) / 8 * 8, nullptr) + 256;
+}
+
+int gb200_stream_diag_update(void* workspace, const void* samples, int64_t Tb, int64_t C, int32_t D, int32_t max_lags,
+                             int64_t T_prev, int32_t dtype, void* stream) {
+  if (!workspace || !samples || Tb < 1 || C < 1 || D < 1 || max_lags < 8 || T_prev < 0 || ((uintptr_t)workspace & 255)) {
+    set_error("stream_diag_update: bad argument (workspace must be 256-byte aligned, max_lags >= 8)");
+    return GB200_ERR_INVALID_ARGUMENT;
+  }
+  if (dtype != GB200_F32 && dtype != GB200_F64) { set_error("stream_diag_update: bad dtype"); return GB200_ERR_INVALID_ARGUMENT; }
+  const int K = (max_lags + 7) / 8 * 8;
+  StreamWs w;
+  stream_carve((unsigned char*)workspace, C, D, K, &w);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (T_prev == 0) cudaMemsetAsync(w.P, 0, sizeof(double) * (size_t)K * D, s);
+  const long long TS = ((K + Tb + 24) | 1);
+  const size_t sh = sizeof(float) * 32 * (size_t)TS;
+  if (sh > 200 * 1024) { set_error("stream_diag_update: block of %lld samples + %d lags does not fit shared memory; use smaller blocks", (long long)Tb, K); return GB200_ERR_UNSUPPORTED; }
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)D);
+  cudaError_t e;
+  if (dtype == GB200_F32) {
+    e = cudaFuncSetAttribute(k_stream_update<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e == cudaSuccess) k_stream_update<float><<<grid, 256, sh, s>>>((const float*)samples, Tb, C, D, K, T_prev, (int)TS, w);
+  } else {
+    e = cudaFuncSetAttribute(k_stream_update<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e == cudaSuccess) k_stream_update<double><<<grid, 256, sh, s>>>((const double*)samples, Tb, C, D, K, T_prev, (int)TS, w);
+  }
+  if (e != cudaSuccess) { set_error("stream_diag_update: %s", cudaGetErrorString(e)); return GB200_ERR_CUDA; }
+  GB_CHECK_LAUNCH();
+  return GB200_OK;
+}
+
+int gb200_stream_diag_partial(void* workspace, int64_t T, int64_t C, int32_t D, int32_t max_lags, int32_t num_lags,
+                              double* stats, double* acov, void* stream) {
+  if (!workspace || !stats || T < 2 || C < 1 || D < 1 || max_lags < 8 || num_lags < 0 || ((uintptr_t)workspace & 255)) {
+    set_error("stream_diag_partial: bad argument");
+    return GB200_ERR_INVALID_ARGUMENT;
+  }
+  const int K = (max_lags + 7) / 8 * 8;
+  if (num_lags > K) num_lags = K;
+  if (num_lags > T) num_lags = (int32_t)T;
+  StreamWs w;
+  stream_carve((unsigned char*)workspace, C, D, K, &w);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(stats, 0, sizeof(double) * (3 * D + 1), s);
+  if (acov && num_lags > 0) cudaMemsetAsync(acov, 0, sizeof(double) * (size_t)num_lags * D, s);
+  dim3 grid((unsigned)((C + 255) / 256), (unsigned)D);
+  k_stream_partial<<<grid, 256, 0, s>>>(T, C, D, K, num_lags, w, stats, (acov && num_lags > 0) ? acov : nullptr);
   GB_CHECK_LAUNCH();
   return GB200_OK;
 }

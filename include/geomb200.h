@@ -225,6 +225,18 @@ int gb200_ess_partial(const void* samples, int64_t T, int64_t C, int32_t D, int3
 int gb200_ess_finalize(const double* acov_host, const double* rhat_stats_host, int64_t T, int64_t C_total, int32_t D,
                        int32_t num_lags, double* ess_host, uint8_t* truncated_host);
 
+/* ---- streaming R-hat / ESS (geomjax/diagnostics.py:25-209 without the [T, C, D] sample tensor) ----------------
+ * Samples are fed in blocks [Tb, C, D] (e.g. the sample buffer of one fused launch, reused); the workspace keeps per
+ * series the shift, sum, sum of squares and the first / last `max_lags` samples, and per (lag, dim) the chain-summed
+ * lagged products.  gb200_stream_diag_partial then yields exactly the statistics of gb200_rhat_partial (stats) and
+ * gb200_ess_partial (acov, num_lags <= max_lags rounded up to 8): all-reduce them over ranks and finalise as usual.
+ * T_prev = samples already fed (0 on the first block: resets the accumulators); T = total fed. */
+int64_t gb200_stream_diag_workspace(int64_t C, int32_t D, int32_t max_lags);
+int gb200_stream_diag_update(void* workspace, const void* samples, int64_t Tb, int64_t C, int32_t D, int32_t max_lags,
+                             int64_t T_prev, int32_t dtype, void* stream);
+int gb200_stream_diag_partial(void* workspace, int64_t T, int64_t C, int32_t D, int32_t max_lags, int32_t num_lags,
+                              double* stats, double* acov, void* stream);
+
 /* ---- batched metric evaluation: vmap(metric_fn)(position) -------------------------------------
  * metric_fn of the logistic-regression target (the reference calls metric_fn at every kinetic-energy /
  * velocity evaluation: rmhmc/metrics.py:46,62,121): G_c = X^T diag(s(1-s)) X + alpha I for every chain,

@@ -113,3 +113,46 @@ def test_window_adaptation_lmcmonge(cuda):
     assert 0.3 < float(info2.acceptance_rate.mean()) <= 1.0
     with pytest.raises(NotImplementedError):
         g.window_adaptation(g.rmhmc, target, num_integration_steps=4)
+
+
+@pytest.mark.parametrize("T_,Cn,D,rho,block", [(300, 40, 3, 0.6, 37), (1000, 130, 5, 0.9, 256), (64, 7, 2, 0.0, 64), (50, 33, 1, 0.5, 8)])
+def test_streaming_diagnostics_equal_batch(cuda, T_, Cn, D, rho, block):
+    """N2: rhat / ess from blocks of samples (no (T, C, D) tensor) == the batch functions on the whole tensor."""
+    import torch
+    import geomjax_b200 as g
+    rng = np.random.default_rng(T_ + Cn)
+    x = np.empty((T_, Cn, D), np.float32)
+    x[0] = rng.standard_normal((Cn, D))
+    for t in range(1, T_):
+        x[t] = rho * x[t - 1] + np.sqrt(1 - rho * rho) * rng.standard_normal((Cn, D))
+    x += np.array([0.0, 100.0, -3.0, 7.0, 1e3][:D], np.float32)  # means far from zero: the shift matters
+    xt = torch.from_numpy(x).to(cuda)
+    lags = 64 if T_ >= 64 else 48
+    sd = g.StreamingDiagnostics(Cn, D, max_lags=lags, device=cuda)
+    for t0 in range(0, T_, block):
+        sd.update(xt[t0:t0 + block])
+    np.testing.assert_allclose(sd.rhat().numpy(), g.rhat(xt, chain_axis=1, sample_axis=0).numpy(), rtol=1e-5)
+    want = g.ess(xt, chain_axis=1, sample_axis=0, initial_lags=lags)
+    got = sd.ess(allow_truncated=True)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-4)
+    np.testing.assert_allclose(got.numpy(), OD.effective_sample_size(x.astype(np.float64), chain_axis=1, sample_axis=0),
+                               rtol=5e-3)
+
+
+def test_sample_streaming_equals_fused_run(cuda):
+    """the blocked driver reproduces one fused launch bit for bit and its diagnostics match the batch ones"""
+    import torch
+    import geomjax_b200 as g
+    D, Cn, Tn = 5, 256, 200
+    mean = torch.arange(D, dtype=torch.float32, device=cuda)
+    target = g.gaussian(mean, torch.tensor([0.25, 1.0, 4.0, 1.0, 2.0], device=cuda))
+    alg = g.lmc(target, 0.3, target, 5)
+    root = g.random.PRNGKey(7)
+    st0 = alg.init(mean.repeat(Cn, 1).contiguous())
+    st_a, samples, acc_a = g.run_fused(alg.step, root, st0, Tn, return_samples=True, return_accept=True)
+    seen = []
+    st_b, diag, acc_b = g.sample_streaming(alg.step, root, st0, Tn, block=48, on_block=lambda f, blk: seen.append(blk.clone()))
+    assert bool((st_a.position == st_b.position).all()) and bool((torch.cat(seen) == samples).all())
+    np.testing.assert_allclose(acc_b.cpu().numpy(), acc_a.mean(0).cpu().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(diag.rhat().numpy(), g.rhat(samples, chain_axis=1, sample_axis=0).numpy(), rtol=1e-5)
+    np.testing.assert_allclose(diag.ess(allow_truncated=True).numpy(), g.ess(samples, chain_axis=1, sample_axis=0).numpy(), rtol=1e-3)

@@ -1,0 +1,130 @@
+"""Full-chain statistical parity (BASELINE.json north_star, part 2): posterior moments of the CUDA chains agree with
+the oracle's chains / the analytic posterior within Monte-Carlo standard error, and the chains mix (R-hat).
+examples/funnel/main.py:57-80 is the shape of these runs: inference loop over `num_samples` keys, then rhat / ess."""
+import numpy as np
+import pytest
+
+from oracle import cpu, diagnostics as OD, prng as P, samplers as S, targets as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _mcse(samples_tcd, ess):
+    """sd / sqrt(ESS) per dimension of (T, C, D) samples."""
+    return samples_tcd.reshape(-1, samples_tcd.shape[-1]).std(0) / np.sqrt(np.maximum(ess, 1.0))
+
+
+def _moments_agree(a, b, k=5.0, what=""):
+    """|mean_a - mean_b| <= k sqrt(MCSE_a^2 + MCSE_b^2) and the same for the second moment, per dimension."""
+    for f, name in ((lambda x: x, "mean"), (lambda x: x * x, "second moment")):
+        xa, xb = f(a), f(b)
+        ea = OD.effective_sample_size(xa, chain_axis=1, sample_axis=0)
+        eb = OD.effective_sample_size(xb, chain_axis=1, sample_axis=0)
+        ma, mb = xa.mean((0, 1)), xb.mean((0, 1))
+        tol = k * np.sqrt(_mcse(xa, ea) ** 2 + _mcse(xb, eb) ** 2)
+        assert (np.abs(ma - mb) <= tol).all(), (what, name, ma, mb, tol)
+
+
+def test_c1_as_shipped_chain_vs_oracle_chain(cuda):
+    """examples/funnel/main.py:57-80 as shipped: lmc + funnel metric, 8 chains, eps = 0.1, L = 8, ones(2), PRNGKey(0),
+    1000 samples.  CUDA chain vs the oracle's chain on the same key tree: the first transitions coincide, later the
+    trajectories decorrelate (float32 chaos), so the comparison is on posterior moments within 5 MCSE."""
+    import torch
+    import geomjax_b200 as g
+    C, Tn = 8, 1000
+    target = g.neal_funnel(2)
+    alg = g.lmc(target, 0.1, target.fisher_metric_fn, 8)
+    root = g.random.PRNGKey(0)
+    _, samples, acc = g.run_fused(alg.step, root, alg.init(torch.ones((C, 2), device=cuda)), Tn, return_samples=True,
+                                  return_accept=True)
+    got = samples.cpu().numpy()
+    smp = cpu.CpuSampler("lmc", 2, 0.1, 8)  # closed-form twin of the NumPy oracle (tests/test_oracle_cpp.py)
+    st = smp.init(np.ones((C, 2), np.float32))
+    want = np.empty((Tn, C, 2), np.float32)
+    oacc = []
+    for t in range(Tn):
+        oacc.append(smp.step(S.chain_keys(P.key(0), Tn, t, C), st)["acceptance_rate"].mean())
+        want[t] = st[0]
+    # same keys, same arithmetic up to round-off: the first transitions are the same chain
+    np.testing.assert_allclose(got[:3], want[:3], rtol=2e-4, atol=2e-5)
+    assert abs(float(acc.mean()) - float(np.mean(oacc))) < 0.03
+    _moments_agree(got[100:], want[100:], what="c1 as shipped")
+
+
+def test_c1_softabs_chain_vs_oracle_chain(cuda):
+    """BASELINE configs[0]: funnel D = 2, rmhmc + SoftAbs metric, 4 chains; CUDA vs the NumPy oracle's chain."""
+    import torch
+    import geomjax_b200 as g
+    C, Tn, eps, L = 4, 400, 0.1, 8
+    target = g.neal_funnel(2)
+    alg = g.rmhmc(target, eps, g.softabs(target, 1e6), L)
+    root = g.random.PRNGKey(0)
+    _, samples, acc = g.run_fused(alg.step, root, alg.init(torch.ones((C, 2), device=cuda)), Tn, return_samples=True,
+                                  return_accept=True)
+    got = samples.cpu().numpy()
+    tgt = T.softabs_metric(T.NealFunnel(2), 1e6)
+    with np.errstate(all="ignore"):
+        _, want, oacc = S.inference_loop(P.key(0), lambda k, s: S.rmhmc_step(k, s, tgt, eps, L),
+                                         S.rmhmc_init(np.ones((C, 2), np.float32), tgt), Tn)
+    assert abs(float(acc.mean()) - float(oacc.mean())) < 0.06
+    _moments_agree(got[50:], want[50:], k=6.0, what="c1 softabs")
+
+
+def test_funnel_d20_lmcmonge_posterior(cuda):
+    """Neal's funnel D = 20 with lmcmonge (alpha2 restored: half_step_omega_fixed, bench/configs.json step size):
+    the posterior is known in closed form (v ~ N(0, 9), x_k | v ~ N(0, e^v)); chains mix (R-hat) and the v / x
+    moments sit within 5 MCSE of the analytic values."""
+    import torch
+    import geomjax_b200 as g
+    D, C, Tn, burn = 20, 1024, 30000, 3000
+    target = g.neal_funnel(D)
+    alg = g.lmcmonge(target, 0.3509, torch.ones(D, device=cuda), 8, integrator=g.integrators.half_step_omega_fixed)
+    st = alg.init(torch.ones((C, D), device=cuda))
+    st, _, _ = g.run_fused(alg.step, g.random.PRNGKey(3), st, burn, total=burn + Tn)
+    st, samples, acc = g.run_fused(alg.step, g.random.PRNGKey(3), st, Tn, first=burn, total=burn + Tn,
+                                   return_samples=True, return_accept="mean")
+    rhat = g.rhat(samples, chain_axis=1, sample_axis=0)
+    ess = g.ess(samples, chain_axis=1, sample_axis=0)
+    assert float(rhat.max()) < 1.01, rhat
+    m = samples.mean(dim=(0, 1)).cpu().numpy()
+    sd = samples.reshape(-1, D).std(0).cpu().numpy()
+    mcse = sd / np.sqrt(ess.cpu().numpy())
+    assert (np.abs(m) <= 5 * mcse).all(), (m, mcse)          # E[v] = 0, E[x_k] = 0
+    v = samples[..., -1]
+    v2 = (v * v)
+    ess_v2 = g.ess(v2.unsqueeze(-1), chain_axis=1, sample_axis=0)
+    mcse_v2 = float(v2.std()) / np.sqrt(float(ess_v2.min()))
+    assert abs(float(v2.mean()) - 9.0) <= 5 * mcse_v2, (float(v2.mean()), mcse_v2)   # Var[v] = sigma^2 = 9
+    assert 0.5 < float(acc.mean()) < 0.99
+
+
+def test_logreg_d25_posterior_vs_oracle(cuda):
+    """Bayesian logistic regression D = 25, N = 1000 (c4's shape and data): R-hat < 1.01 and posterior means /
+    second moments within 5 MCSE of a run of the CPU restatement (oracle/cpp, checked against the NumPy oracle)."""
+    import torch
+    import geomjax_b200 as g
+    N_, D, L, eps = 1000, 25, 6, 0.1
+    X, y = T.make_logreg_data(N_, D, seed=0)
+    target = g.logistic_regression(torch.from_numpy(X).to(cuda), torch.from_numpy(y).to(cuda), 0.01)
+    alg = g.rmhmc(target, eps, target, L)
+    C, Tn, burn = 2048, 160, 24
+    st = alg.init(torch.zeros((C, D), device=cuda))
+    st, samples, acc = g.run_fused(alg.step, g.random.PRNGKey(11), st, burn + Tn, return_samples=True,
+                                   return_accept="mean")
+    x = samples[burn:]
+    rhat = g.rhat(x, chain_axis=1, sample_axis=0)
+    assert float(rhat.max()) < 1.01, rhat
+    assert float(acc.mean()) > 0.9
+    # CPU restatement: 32 chains x (24 + 120) transitions
+    smp = cpu.CpuSampler("rmhmc", D, eps, L, X=X, y=y, prior_precision=0.01)
+    Co, To = 32, 120
+    ost = smp.init(np.zeros((Co, D), np.float32))
+    smp.run(P.key(5), ost, burn, total=burn + To)
+    want = np.empty((To, Co, D), np.float32)
+    for t in range(To):
+        smp.step(S.chain_keys(P.key(5), burn + To, burn + t, Co), ost, want_info=False)
+        want[t] = ost[0]
+    got = x.cpu().numpy()
+    _moments_agree(got[:, :256], want, what="logreg D=25")
+    # and against the GPU's own full chain set (tighter MCSE): the 256-chain subset is representative
+    np.testing.assert_allclose(got.mean((0, 1)), got[:, :256].mean((0, 1)), atol=0.05)
