@@ -307,22 +307,31 @@ def timed_e2e(cx, alg, C, D, TPS, K, W, start_position, min_warm=2):
     return cx.max_over_ranks(e0.elapsed_time(e1)), acc, C * D * 4, C * D * 4 + C * 4
 
 
-def ess_record(cx, alg, C, D, Tn, burnin, init_fill):
-    """A sampling run that keeps every sample on the device (buffer allocated BEFORE the timed region), then the
-    sharded R-hat / ESS.  min_ess_per_s is only reported when the chains have mixed (max R-hat < 1.01)."""
+def ess_record(cx, alg, C, D, Tn, burnin, init_fill, thin=1):
+    """A sampling run that keeps every (thin-th) sample on the device (buffer allocated BEFORE the timed region), then
+    the sharded R-hat / ESS.  min_ess_per_s is only reported when the chains have mixed (max R-hat < 1.01).  thin > 1:
+    one fused launch of `thin` transitions per recorded sample; the ESS of the thinned chain is a lower bound of the
+    full chain's."""
     g, torch = cx.g, cx.torch
     Tn = max(16, min(Tn, int(24e9 // (C * D * 4))))  # the sample tensor stays <= 24 GB (c3: 131,072 x 100 per GPU)
     st = alg.init(init_fill((C, D), device=cx.dev))
     samples = torch.empty((Tn, C, D), device=cx.dev)
     acc = torch.empty((C,), device=cx.dev)
+    total = burnin + Tn * thin
+    kw = dict(total=total, chain_offset=cx.rank * C, total_chains=C * cx.world)
     if burnin > 0:
-        st, _, _ = g.run_fused(alg.step, cx.root, st, burnin, first=0, total=burnin + Tn, chain_offset=cx.rank * C,
-                               total_chains=C * cx.world, inplace=True)
+        st, _, _ = g.run_fused(alg.step, cx.root, st, burnin, first=0, inplace=True, **kw)
     cx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    st, _, _ = g.run_fused(alg.step, cx.root, st, Tn, first=burnin, total=burnin + Tn, chain_offset=cx.rank * C,
-                           total_chains=C * cx.world, out_samples=samples, return_accept="mean", out_accept=acc)
+    if thin == 1:
+        st, _, _ = g.run_fused(alg.step, cx.root, st, Tn, first=burnin, out_samples=samples, return_accept="mean",
+                               out_accept=acc, **kw)
+    else:
+        for t in range(Tn):
+            st, _, _ = g.run_fused(alg.step, cx.root, st, thin, first=burnin + t * thin, inplace=True,
+                                   return_accept="mean", out_accept=acc, **kw)
+            samples[t].copy_(st.position)
     e1.record()
     torch.cuda.synchronize()
     samp_ms = cx.max_over_ranks(e0.elapsed_time(e1))
@@ -333,13 +342,13 @@ def ess_record(cx, alg, C, D, Tn, burnin, init_fill):
     d1.record()
     torch.cuda.synchronize()
     max_rhat, min_ess = float(rhat.max()), float(ess.min())
-    rec = {"max_rhat": max_rhat, "min_ess": min_ess, "samples_per_chain": Tn, "burnin": burnin,
+    rec = {"max_rhat": max_rhat, "min_ess": min_ess, "samples_per_chain": Tn, "thinning": thin, "burnin": burnin,
            "sampling_ms": samp_ms, "diagnostics_ms": d0.elapsed_time(d1), "mean_acceptance": float(acc.mean()),
            "min_ess_valid": bool(max_rhat < 1.01)}
     if rec["min_ess_valid"]:
         rec["min_ess_per_s"] = min_ess / (samp_ms * 1e-3)
     else:
-        rec["min_ess_invalid_reason"] = f"max R-hat {max_rhat:.4f} >= 1.01 after {burnin}+{Tn} transitions: chains have not mixed"
+        rec["min_ess_invalid_reason"] = f"max R-hat {max_rhat:.4f} >= 1.01 after {burnin}+{Tn * thin} transitions: chains have not mixed"
     del samples
     return rec
 
@@ -381,7 +390,7 @@ def funnel_flops(cx, cfg, alg, sampler_id, target, state, C):
 
 
 def bench_funnel(cx, args, cfg, wl_key, *, half_step=None, step_size=None, C=None, TPS=None, K=None, W=None,
-                 with_e2e=True, ess_samples=0, burnin=0):
+                 with_e2e=True, ess_samples=0, burnin=0, thin=1):
     """Device-resident + e2e + roofline (+ R-hat / ESS) for one funnel workload."""
     g, torch, N = cx.g, cx.torch, cx.N
     D, L = cfg["D"], cfg["num_integration_steps"]
@@ -433,7 +442,7 @@ def bench_funnel(cx, args, cfg, wl_key, *, half_step=None, step_size=None, C=Non
             nominal_source=f"148 SMs x 128 lanes x 2 x {clk or 1965.0:.0f} MHz (median SM clock of this run)",
             kernel_ms_median=med, **frec)
     if ess_samples > 0:
-        rec.update(ess_record(cx, alg, C, D, ess_samples, burnin, init_fill))
+        rec.update(ess_record(cx, alg, C, D, ess_samples, burnin, init_fill, thin))
     return rec
 
 
@@ -602,14 +611,16 @@ def run_ours(args, cfg):
         try:
             if s == "c2_omega_fixed" and args.workload == "c2":
                 workloads[s] = bench_funnel(cx, args, CONFIGS["c2"], "c2", half_step="omega_fixed", TPS=256, K=5, W=3,
-                                            with_e2e=False, ess_samples=4 * args.ess_samples, burnin=5 * args.ess_burnin)
+                                            with_e2e=False, ess_samples=4 * args.ess_samples, burnin=16384, thin=64)
                 workloads[s]["note"] = ("c2 with alpha2 restored on the Christoffel correction (half_step_omega_fixed, eps "
                                         "from the same warm-up recipe): the variant that can mix; the headline runs the "
                                         "reference AS WRITTEN (lmcmonge/integrators.py:186-189, SURVEY F8), which only "
-                                        "accepts at eps ~ 1e-3 and therefore cannot mix in 1000 transitions")
+                                        "accepts at eps ~ 1e-3 and therefore cannot mix in 1000 transitions.  The nearly "
+                                        "Euclidean Monge metric (alpha2 = 1e-3) decorrelates the funnel's v over ~2,600 "
+                                        "transitions, so this record thins by 64 to pass the R-hat gate")
             elif s == "c4":
                 workloads[s] = bench_logreg(cx, args, CONFIGS["c4"], C=CONFIGS["c4"]["chains_per_gpu"], T=16, K=3, W=1,
-                                            label=CONFIGS["c4"]["name"], ess_samples=min(args.ess_samples, 192), burnin=32)
+                                            label=CONFIGS["c4"]["name"], ess_samples=min(args.ess_samples, 640), burnin=40)
             elif s == "c5_shard":
                 c5 = CONFIGS["c5_shard"]
                 workloads[s] = bench_logreg(cx, args, c5, C=c5["chains_per_gpu"], T=2, K=2, W=1, label=c5["name"])

@@ -8,8 +8,10 @@ hand-written CUDA for sm_100a behind the C ABI of ``include/geomb200.h``.
 from . import integrators, random, targets  # noqa: F401
 from .adaptation import dual_averaging, step_size_adaptation, window_adaptation  # noqa: F401
 from .base import AdaptationAlgorithm, AdaptationResults, SamplingAlgorithm  # noqa: F401
-from .samplers import (LMCInfo, LMCState, Proposal, RMHMCInfo, RMHMCState, lmc, lmcmonge, rmhmc,  # noqa: F401
-                       run_fused)
+from .samplers import (DynamicLMCState, DynamicRMHMCState, LMCInfo, LMCState, Proposal, RMHMCInfo,  # noqa: F401
+                       RMHMCState, dynamic_lmc, dynamic_lmcmonge, dynamic_rmhmc, lmc, lmcmonge, rmhmc, run_fused)
+from .chees import chees_adaptation as chees_adaptation_riemanian  # noqa: F401
+from . import chees  # noqa: F401
 from .plan import LockstepPlan  # noqa: F401
 from .diagnostics import effective_sample_size as ess  # noqa: F401
 from .diagnostics import potential_scale_reduction as rhat  # noqa: F401

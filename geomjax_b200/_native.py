@@ -37,7 +37,8 @@ class KernelParams(C.Structure):
                 ("fp_divergence_tol", C.c_double), ("fp_max_iters", C.c_int32), ("half_step", C.c_int32),
                 ("alpha2", C.c_double), ("inverse_mass_matrix", vp),
                 ("dtype", C.c_int32), ("lanes_per_chain", C.c_int32),
-                ("inverse_mass_per_chain", C.c_int32), ("reserved", C.c_int32)]
+                ("inverse_mass_per_chain", C.c_int32), ("reserved", C.c_int32),
+                ("num_integration_steps_per_chain", vp)]
 
 
 class State(C.Structure):
@@ -107,6 +108,8 @@ PROTOTYPES = {
     "gb200_stream_diag_workspace": (_i64, [_i64, _i32, _i32]),
     "gb200_stream_diag_update": (C.c_int, [vp, vp, _i64, _i64, _i32, _i32, _i64, _i32, vp]),
     "gb200_stream_diag_partial": (C.c_int, [vp, _i64, _i64, _i32, _i32, _i32, vp, vp, vp]),
+    "gb200_chees_moments": (C.c_int, [vp, vp, vp, vp, _i64, _i32, vp, vp]),
+    "gb200_chees_gradient": (C.c_int, [vp, vp, vp, vp, vp, vp, _i64, _i32, vp, vp]),
     "gb200_fp32_peak_kernel": (C.c_int, [vp, _i32, _i32, _i64, vp]),
     "gb200_flops_per_chain_step": (_dbl, [_i32, _P(TargetDesc)]),
     "gb200_flops_per_transition": (_dbl, [_i32, _P(TargetDesc)]),

@@ -209,6 +209,7 @@ int gb200_step(int32_t sampler, const gb200_kernel_params* p, const gb200_target
   a.fp_div_tol = p->fp_divergence_tol;
   a.fp_max_iters = p->fp_max_iters;
   a.num_steps = p->num_integration_steps;
+  a.steps_per_chain = p->num_integration_steps_per_chain;
   a.half_step = p->half_step;
   a.D = target->D;
   a.metric = target->metric;
@@ -218,6 +219,7 @@ int gb200_step(int32_t sampler, const gb200_kernel_params* p, const gb200_target
   if (target->kind == GB200_TARGET_LOGREG) {
     if (sampler != GB200_RMHMC) { set_error("logreg: only rmhmc (Fisher metric) is built in this version"); return GB200_ERR_UNSUPPORTED; }
     if (opts && opts->plan) return launch_rmhmc_lockstep(a, *target, (gb200_plan*)opts->plan, p->dtype, (cudaStream_t)stream);
+    if (a.steps_per_chain) { set_error("logreg: per-chain num_integration_steps needs the lock-step plan (gb200_run_opts.plan)"); return GB200_ERR_UNSUPPORTED; }
     return launch_rmhmc_logreg(a, *target, p->dtype, (cudaStream_t)stream);
   }
   if (target->metric == GB200_METRIC_SOFTABS && sampler != GB200_RMHMC) {

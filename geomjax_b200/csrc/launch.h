@@ -19,7 +19,8 @@ GB_DECL_LPC(1) GB_DECL_LPC(2) GB_DECL_LPC(4) GB_DECL_LPC(8) GB_DECL_LPC(32)
 inline bool lean_launch(const TransArgs& a) {
   const gb200_info& f = a.info;
   return a.mode == GB200_THREEFRY_LEGACY && a.opts.noise_override == nullptr && a.opts.uniform_override == nullptr &&
-         a.opts.dual_averaging == nullptr && a.step_size_per_chain == nullptr && !f.noise && !f.momentum &&
+         a.opts.dual_averaging == nullptr && a.step_size_per_chain == nullptr && a.steps_per_chain == nullptr &&
+         !f.noise && !f.momentum &&
          !f.acceptance_rate && !f.is_accepted && !f.is_divergent && !f.energy && !f.proposal_position &&
          !f.proposal_velocity && !f.proposal_momentum && !f.proposal_logdensity && !f.proposal_logdensity_grad &&
          !f.proposal_volume_adjustment && !f.proposal_weight && !f.initial_energy && !f.accept_uniform && !f.fp_iters;

@@ -192,13 +192,33 @@ __global__ void __launch_bounds__(128) lmc_kernel(const TransArgs a, const Targe
 
     // one_step lmcmc/integrators.py:93-142 = half-step, position + gradient refresh, half-step; written
     // as 2L half-steps so that the half-step body exists once in the instruction stream.
-    const int nh = 2 * a.num_steps;
+    // Dynamic kernels (lmcmc/lmc.py:185-252): a per-chain step count.  The warp runs to its largest count; a chain
+    // that is done discards the half-step (masked commit) and moves by 0 * u, so its state stays bit-identical.
+    int nh_chain = 2 * a.num_steps, nh = nh_chain;
+    if (!LEAN && a.steps_per_chain != nullptr) {
+      nh_chain = 2 * a.steps_per_chain[chain];
+      nh = __reduce_max_sync(0xffffffffu, nh_chain);
+    }
 #pragma unroll 1
     for (int h = 0; h < nh; ++h) {
-      J += Metric::half_step(lay, tg, ctx, q, g, u, eps);
+      const bool live = LEAN || h < nh_chain;
+      const R eps_h = live ? eps : R(0);
+      if (LEAN) {
+        J += Metric::half_step(lay, tg, ctx, q, g, u, eps);
+      } else {
+        R un[EPL];
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) un[k] = u[k];
+        const R dJ = Metric::half_step(lay, tg, ctx, q, g, un, eps);
+        if (live) {
+#pragma unroll
+          for (int k = 0; k < EPL; ++k) u[k] = un[k];
+          J += dJ;
+        }
+      }
       if (!(h & 1)) {
 #pragma unroll
-        for (int k = 0; k < EPL; ++k) q[k] = fma(eps, u[k], q[k]);
+        for (int k = 0; k < EPL; ++k) q[k] = fma(eps_h, u[k], q[k]);
         ctx = tg.prepare(lay, q);
         lp = tg.logp(ctx);
         tg.grad(lay, ctx, q, g);

@@ -235,13 +235,21 @@ __global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const 
     // ---- L integrator steps: lmcmonge/integrators.py:63-153.  One step = half-step, position /
     // gradient / HVP refresh, half-step, Hv refresh; written as 2L half-steps so that the half-step
     // body exists once in the instruction stream (same operations in the same order).
-    const int nh = 2 * a.num_steps;
+    // Dynamic kernels (lmcmonge/lmc.py build_dynamic_kernel): a per-chain step count.  The warp runs to its largest
+    // count; a chain that is done keeps stepping with step size 0, which is an exact no-op of every update below
+    // (v - 0 * x, q + 0 * v, log|1 + 0|), so its state is bit-identical to having stopped.
+    int nh_chain = 2 * a.num_steps, nh = nh_chain;
+    if (!LEAN && a.steps_per_chain != nullptr) {
+      nh_chain = 2 * a.steps_per_chain[chain];
+      nh = __reduce_max_sync(0xffffffffu, nh_chain);
+    }
 #pragma unroll 1
     for (int h = 0; h < nh; ++h) {
-      monge_half_step<R, EPL, LPC, UNIT>(half_step, a2, m, J, L, sL, rs, eps);
+      const R eps_h = (LEAN || h < nh_chain) ? eps : R(0);
+      monge_half_step<R, EPL, LPC, UNIT>(half_step, a2, m, J, L, sL, rs, eps_h);
       if (!(h & 1)) {
 #pragma unroll
-        for (int k = 0; k < EPL; ++k) q[k] = fma(eps, m.v[k], q[k]);
+        for (int k = 0; k < EPL; ++k) q[k] = fma(eps_h, m.v[k], q[k]);
         ctx = tg.prepare(lay, q);
         lp = tg.logp(ctx);
         if constexpr (UNIT && Target::kGradSqnorm) {

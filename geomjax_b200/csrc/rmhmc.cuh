@@ -185,7 +185,16 @@ __global__ void __launch_bounds__(128) rmhmc_kernel(const TransArgs a, const Tar
     const R H0 = -l0 + Metric::kinetic(lay, tg, ctx, q, p);  // hmc_energy
     int iters_total = 0;
 
-    for (int s = 0; s < a.num_steps; ++s) {  // implicit_midpoint.one_step rmhmc/integrators.py:116-154
+    // Dynamic kernels (rmhmc/rmhmc.py:179-244): a per-chain step count.  The warp runs to its largest count; a chain
+    // that is done steps with half step 0: the map returns its argument, the fixed point converges at once.
+    int L_chain = a.num_steps, L_warp = a.num_steps;
+    if (!LEAN && a.steps_per_chain != nullptr) {
+      L_chain = a.steps_per_chain[chain];
+      L_warp = __reduce_max_sync(0xffffffffu, L_chain);
+    }
+    const R he_full = he;
+    for (int s = 0; s < L_warp; ++s) {  // implicit_midpoint.one_step rmhmc/integrators.py:116-154
+      const R he = s < L_chain ? he_full : R(0);
       R q0[EPL], p0[EPL], qn[EPL], pn[EPL];
 #pragma unroll
       for (int k = 0; k < EPL; ++k) { q0[k] = q[k]; p0[k] = p[k]; }

@@ -594,6 +594,11 @@ __global__ void __launch_bounds__(256) ls_advance_kernel(const LsBuf b, const Ls
       pw = ls_warp_sum(pw);
       if (lane == 0) b.H0[c] = -((const float*)a.out_logp)[c] + 0.5f * pw + 0.5f * b.logdet[j] + half_log_2pi * (float)D;
     }
+    if (ph == LS_PH_FIRST0 && a.steps_per_chain != nullptr && a.steps_per_chain[c] <= 0) {
+      // dynamic kernel drew zero integration steps: the proposal is the initial state (mcmc/trajectory.py:137)
+      if (lane == 0) b.phase[c] = LS_PH_END;
+      return;
+    }
 #pragma unroll
     for (int k = 0; k < EP; ++k) {
       const int i = lane + 32 * k;
@@ -628,7 +633,8 @@ __global__ void __launch_bounds__(256) ls_advance_kernel(const LsBuf b, const Ls
     if (lane == 0) {
       const int s = b.step[c] + 1;
       b.step[c] = s;
-      b.phase[c] = s < a.num_steps ? LS_PH_FIRST : LS_PH_END;
+      const int Lc = a.steps_per_chain != nullptr ? a.steps_per_chain[c] : a.num_steps;  // dynamic kernels: per chain
+      b.phase[c] = s < Lc ? LS_PH_FIRST : LS_PH_END;
     }
   } else {  // LS_PH_END: energy of the proposal, accept, outputs (rmhmc/rmhmc.py:416-438, mcmc/proposal.py)
     float qq = 0.f, pw = 0.f;

@@ -23,6 +23,7 @@ struct TransArgs {
   double fp_tol, fp_div_tol;
   int fp_max_iters;
   int num_steps;
+  const int* steps_per_chain;  // optional [C]: per-chain number of integrator steps (dynamic kernels); num_steps = their upper bound
   int half_step;
   int D;
   int metric;  // gb200_metric_kind

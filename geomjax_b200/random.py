@@ -21,8 +21,15 @@ def threefry_mode() -> int:
 
 
 def PRNGKey(seed: int) -> np.ndarray:
-    """Raw key data ``[hi32(seed), lo32(seed)]`` (host array; root keys are tiny)."""
-    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    """Raw key data ``[hi32(seed), lo32(seed)]`` (host array; root keys are tiny).  As in JAX with x64 disabled (the
+    reference's configuration) a negative seed is an int32: ``PRNGKey(-1) == [0, 0xFFFFFFFF]``; seeds >= 2**32 keep
+    their high word (JAX's x64 behaviour; JAX without x64 raises for them)."""
+    seed = int(seed)
+    if seed < 0:
+        if seed < -(1 << 31):
+            raise OverflowError("negative seeds must fit int32 (JAX with x64 disabled)")
+        return np.array([0, seed & 0xFFFFFFFF], dtype=np.uint32)
+    seed &= 0xFFFFFFFFFFFFFFFF
     return np.array([seed >> 32, seed & 0xFFFFFFFF], dtype=np.uint32)
 
 
@@ -68,6 +75,22 @@ def uniform(keys, count: int = 1, device=None) -> torch.Tensor:
 
 def normal(keys, count: int, device=None) -> torch.Tensor:
     return _draw(N.lib().gb200_normal_f32, keys, count, torch.float32, device)
+
+
+def randint(keys, minval: int, maxval: int, device=None) -> torch.Tensor:
+    """``jax.random.randint(key, (), minval, maxval)`` for a batch of keys (..., 2) -> (...,) int32
+    (jax/_src/random.py ``_randint``: two 32-bit draws from ``split(key)``, combined modulo the span with the
+    multiplier 2**32 % span so that the result is uniform over the 64-bit draw).  The default
+    ``integration_steps_fn`` of the dynamic kernels (rmhmc/rmhmc.py:183, lmcmc/lmc.py:189)."""
+    k = _keys_tensor(keys, device)
+    ks = split(k, 2)
+    hi = bits(ks[..., 0, :].contiguous(), 1)[..., 0].to(torch.int64)
+    lo = bits(ks[..., 1, :].contiguous(), 1)[..., 0].to(torch.int64)
+    span = max(int(maxval) - int(minval), 1) if maxval > minval else 1
+    mult = ((1 << 16) % span) ** 2 % span
+    M32 = (1 << 32) - 1
+    off = ((((hi % span) * mult) & M32) + (lo % span)) & M32  # uint32 wrap-around, as in lax
+    return (int(minval) + off % span).to(torch.int32)
 
 
 def chain_keys(root_key, t: int, total_transitions: int, num_chains: int, chain_offset: int = 0,

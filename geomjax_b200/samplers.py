@@ -27,8 +27,8 @@ from . import random as grandom
 from .base import SamplingAlgorithm
 from .targets import as_target
 
-__all__ = ["rmhmc", "lmc", "lmcmonge", "RMHMCState", "RMHMCInfo", "LMCState", "LMCInfo", "Proposal",
-           "run_fused"]
+__all__ = ["rmhmc", "lmc", "lmcmonge", "dynamic_rmhmc", "dynamic_lmc", "dynamic_lmcmonge", "RMHMCState", "RMHMCInfo",
+           "LMCState", "LMCInfo", "DynamicRMHMCState", "DynamicLMCState", "Proposal", "run_fused"]
 
 
 class RMHMCState(NamedTuple):
@@ -42,6 +42,21 @@ class LMCState(NamedTuple):
     logdensity: torch.Tensor
     logdensity_grad: torch.Tensor
     volume_adjustment: torch.Tensor
+
+
+class DynamicRMHMCState(NamedTuple):  # rmhmc/rmhmc.py:44-55
+    position: torch.Tensor
+    logdensity: torch.Tensor
+    logdensity_grad: torch.Tensor
+    random_generator_arg: torch.Tensor
+
+
+class DynamicLMCState(NamedTuple):  # lmcmc/lmc.py:45-57, lmcmonge/lmc.py:47-60
+    position: torch.Tensor
+    logdensity: torch.Tensor
+    logdensity_grad: torch.Tensor
+    volume_adjustment: torch.Tensor
+    random_generator_arg: torch.Tensor
 
 
 class RMHMCIntegratorState(NamedTuple):  # rmhmc/integrators.py:25-36
@@ -139,6 +154,11 @@ class _Engine:
         self.sampler = sampler
         self.target = as_target(target)
         self.step_size = step_size
+        # a (C,) integer tensor = per-chain step counts of the dynamic kernels; the scalar passed down is their bound
+        self.steps_per_chain = None
+        if isinstance(num_integration_steps, torch.Tensor) and num_integration_steps.ndim >= 1:
+            self.steps_per_chain = num_integration_steps
+            num_integration_steps = int(num_integration_steps.max()) if num_integration_steps.numel() else 0
         self.L = int(num_integration_steps)
         self.divergence_threshold = float(divergence_threshold)
         if isinstance(inverse_mass_matrix, (torch.Tensor, np.ndarray)) and inverse_mass_matrix.ndim == 1 \
@@ -173,6 +193,12 @@ class _Engine:
         else:
             p.step_size = float(ss)
         p.num_integration_steps = self.L
+        if self.steps_per_chain is not None:
+            spc = self.steps_per_chain.to(device=ref.device, dtype=torch.int32).contiguous()
+            if spc.shape != (ref.shape[0],):
+                raise ValueError("per-chain num_integration_steps must have shape (C,)")
+            p.num_integration_steps_per_chain = N.ptr(spc)
+            keep.append(spc)
         p.threefry_mode = grandom.threefry_mode()
         p.divergence_threshold = self.divergence_threshold
         p.fp_convergence_tol, p.fp_divergence_tol, p.fp_max_iters = self.fp
@@ -451,3 +477,123 @@ class lmcmonge:
                       divergence_threshold=divergence_threshold, inverse_mass_matrix=inverse_mass_matrix,
                       alpha2=alpha2, lanes_per_chain=lanes_per_chain, **integ.kwargs)
         return SamplingAlgorithm(lambda position: cls.init(position, eng.target), _StepFn(eng))
+
+
+# ------------------------------------------------------------------------------------ dynamic kernels
+# rmhmc/rmhmc.py:179-244, lmcmc/lmc.py:185-252, lmcmonge/lmc.py:240-309: the number of integration steps of each
+# transition is drawn by ``integration_steps_fn(state.random_generator_arg)`` and the argument advanced by
+# ``next_random_arg_fn``.  Batched over chains: ``random_generator_arg`` is (C, 2) uint32 keys (the reference's
+# default, every chain its own key) or a (C,) / scalar integer counter (the Halton jitter of ChEES); the step counts
+# go to the kernels as a per-chain array (gb200_kernel_params.num_integration_steps_per_chain) -- a warp runs to its
+# largest count with the finished chains masked.
+
+
+def _default_next_random_arg(arg):
+    return grandom.split(arg, 2)[..., 1, :].contiguous()  # lambda key: jax.random.split(key)[1]
+
+
+def _default_integration_steps(arg):
+    return grandom.randint(arg, 1, 10)  # lambda key: jax.random.randint(key, (), 1, 10)
+
+
+def _steps_tensor(steps, C_, device):
+    if isinstance(steps, torch.Tensor):
+        st = steps.to(device=device, dtype=torch.int32).reshape(-1)
+        return st.expand(C_).contiguous() if st.numel() == 1 else st
+    return int(steps)
+
+
+def _dynamic_kernel_fn(sampler_id):
+    def build_dynamic_kernel(integrator: Callable = None, divergence_threshold: float = 1000,
+                             next_random_arg_fn: Callable = _default_next_random_arg,
+                             integration_steps_fn: Callable = _default_integration_steps):
+        base = _kernel_fn(sampler_id, "dynamic")(integrator, divergence_threshold)
+
+        def finish(new, info, state):
+            return type(state)(*new, next_random_arg_fn(state.random_generator_arg)), info
+
+        if sampler_id == N.LMCMONGE:
+            def kernel(rng_key, state, logdensity_fn, step_size, inverse_mass_matrix, alpha2=0.001,
+                       **integration_steps_kwargs):
+                steps = _steps_tensor(integration_steps_fn(state.random_generator_arg, **integration_steps_kwargs),
+                                      state.position.shape[0], state.position.device)
+                new, info = base(rng_key, LMCState(*state[:4]), logdensity_fn, step_size, inverse_mass_matrix, steps, alpha2)
+                return finish(new, info, state)
+        else:
+            nfields = 3 if sampler_id == N.RMHMC else 4
+            cls = RMHMCState if sampler_id == N.RMHMC else LMCState
+
+            def kernel(rng_key, state, logdensity_fn, step_size, metric_fn, **integration_steps_kwargs):
+                steps = _steps_tensor(integration_steps_fn(state.random_generator_arg, **integration_steps_kwargs),
+                                      state.position.shape[0], state.position.device)
+                new, info = base(rng_key, cls(*state[:nfields]), logdensity_fn, step_size, metric_fn, steps)
+                return finish(new, info, state)
+        return kernel
+
+    return build_dynamic_kernel
+
+
+def _random_arg(arg, C_, device):
+    """one generator argument per chain: (C, 2) keys, a single (2,) key (split into C), or an integer counter"""
+    if isinstance(arg, int):
+        return torch.full((C_,), arg, dtype=torch.int64, device=device)
+    if isinstance(arg, np.ndarray):
+        arg = torch.from_numpy(np.ascontiguousarray(arg))
+    arg = arg.to(device)
+    if arg.dtype in (torch.uint32, torch.int32) and arg.shape == (2,):
+        return grandom.split(arg[None], C_)[0].contiguous()
+    return arg
+
+
+class dynamic_rmhmc:
+    """geomjax/rmhmc/rmhmc.py:314-376."""
+
+    @staticmethod
+    def init(position, logdensity_fn, random_generator_arg):
+        q, l, gr = _init(position, logdensity_fn, False)[:3]
+        return DynamicRMHMCState(q, l, gr, _random_arg(random_generator_arg, q.shape[0], q.device))
+
+    build_kernel = staticmethod(_dynamic_kernel_fn(N.RMHMC))
+
+    def __new__(cls, logdensity_fn, step_size, metric_fn, *, divergence_threshold: int = 1000, integrator: Callable = None,
+                next_random_arg_fn: Callable = _default_next_random_arg,
+                integration_steps_fn: Callable = _default_integration_steps):
+        kernel = cls.build_kernel(integrator, divergence_threshold, next_random_arg_fn, integration_steps_fn)
+        return SamplingAlgorithm(lambda position, random_generator_arg: cls.init(position, logdensity_fn, random_generator_arg),
+                                 lambda rng_key, state: kernel(rng_key, state, logdensity_fn, step_size, metric_fn))
+
+
+class dynamic_lmc:
+    """geomjax/lmcmc/lmc.py:349-408."""
+
+    @staticmethod
+    def init(position, logdensity_fn, random_generator_arg):
+        f = _init(position, logdensity_fn, True)
+        return DynamicLMCState(*f, _random_arg(random_generator_arg, f[0].shape[0], f[0].device))
+
+    build_kernel = staticmethod(_dynamic_kernel_fn(N.LMC))
+
+    def __new__(cls, logdensity_fn, step_size, metric_fn, *, divergence_threshold: int = 1000, integrator: Callable = None,
+                next_random_arg_fn: Callable = _default_next_random_arg,
+                integration_steps_fn: Callable = _default_integration_steps):
+        kernel = cls.build_kernel(integrator, divergence_threshold, next_random_arg_fn, integration_steps_fn)
+        return SamplingAlgorithm(lambda position, random_generator_arg: cls.init(position, logdensity_fn, random_generator_arg),
+                                 lambda rng_key, state: kernel(rng_key, state, logdensity_fn, step_size, metric_fn))
+
+
+class dynamic_lmcmonge:
+    """geomjax/lmcmonge/lmc.py dynamic_lmc (exported as geomjax.dynamic_lmcmonge)."""
+
+    @staticmethod
+    def init(position, logdensity_fn, random_generator_arg):
+        f = _init(position, logdensity_fn, True)
+        return DynamicLMCState(*f, _random_arg(random_generator_arg, f[0].shape[0], f[0].device))
+
+    build_kernel = staticmethod(_dynamic_kernel_fn(N.LMCMONGE))
+
+    def __new__(cls, logdensity_fn, step_size, inverse_mass_matrix, *, alpha2: float = 0.001, divergence_threshold: int = 1000,
+                integrator: Callable = None, next_random_arg_fn: Callable = _default_next_random_arg,
+                integration_steps_fn: Callable = _default_integration_steps):
+        kernel = cls.build_kernel(integrator, divergence_threshold, next_random_arg_fn, integration_steps_fn)
+        return SamplingAlgorithm(lambda position, random_generator_arg: cls.init(position, logdensity_fn, random_generator_arg),
+                                 lambda rng_key, state: kernel(rng_key, state, logdensity_fn, step_size, inverse_mass_matrix, alpha2))

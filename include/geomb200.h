@@ -97,6 +97,9 @@ typedef struct gb200_kernel_params {
   int32_t lanes_per_chain;           /* 0 = auto; else 1,2,4,8,16,32 (tuning knob) */
   int32_t inverse_mass_per_chain;    /* lmcmonge: 0 = inverse_mass_matrix is [D]; 1 = [C, D] (vmapped window adaptation) */
   int32_t reserved;
+  const int32_t* num_integration_steps_per_chain; /* optional [C] (device): the dynamic kernels' per-chain draw of
+                                        integration_steps_fn (rmhmc/rmhmc.py:179-244, lmcmc/lmc.py:185-252);
+                                        num_integration_steps must then be an upper bound of its entries */
 } gb200_kernel_params;
 
 /* RMHMCState / LMCState (rmhmc/rmhmc.py:30-41, lmcmc/lmc.py:30-42, lmcmonge/lmc.py:32-44). */
@@ -280,6 +283,17 @@ int gb200_plan_stats(const gb200_plan* plan, int64_t* rounds, int64_t* chain_eva
 int gb200_logreg_lockstep_eval(gb200_plan* plan, int32_t mode, const void* q, const void* p, const void* qi, const void* pi,
                                double half_step, void* qn, void* pn, void* p_out, void* logdensity, void* logdensity_grad,
                                void* velocity, void* logdet, void* dHdq, int64_t C, void* stream);
+
+/* ---- ChEES adaptation: the cross-chain sums of compute_parameters (adaptation/chees_adaptation_riemanian.py:102-219),
+ * float32 chains.  moments -> out[4 D + 2] = sum / count of the non-NaN proposal and initial positions per dimension,
+ * sum of 1 / acceptance and count over the non-divergent chains; gradient (means[2 D] = the global nanmeans, device)
+ * -> out[2] = sum of acceptance_c g_c and of acceptance_c over the non-divergent chains.  All plain sums: one
+ * all-reduce(sum) per pass combines shards. */
+int gb200_chees_moments(const void* proposal_position, const void* initial_position, const void* acceptance_rate,
+                        const uint8_t* is_divergent, int64_t C, int32_t D, double* out, void* stream);
+int gb200_chees_gradient(const void* proposal_position, const void* proposal_velocity, const void* initial_position,
+                         const void* acceptance_rate, const uint8_t* is_divergent, const double* means, int64_t C, int32_t D,
+                         double* out, void* stream);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Runs a dependent-FMA microbenchmark (iters FFMA per thread on grid x block threads) for the FP32

@@ -55,7 +55,10 @@ def threefry2x32(k0, k1, x0, x1):
 
 def key(seed: int) -> np.ndarray:
     """``jax.random.PRNGKey(seed)`` / ``jax.random.key(seed)`` raw key data: [hi32, lo32]."""
-    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    seed = int(seed)
+    if seed < 0:  # x64 disabled (the reference's configuration): the seed is an int32, its high word is 0
+        return np.array([0, seed & 0xFFFFFFFF], dtype=_U32)
+    seed &= 0xFFFFFFFFFFFFFFFF
     return np.array([seed >> 32, seed & 0xFFFFFFFF], dtype=_U32)
 
 
@@ -220,3 +223,19 @@ def bernoulli(k, p, mode: str = LEGACY):
     k = np.asarray(k, dtype=_U32)
     u = uniform(k, (), mode)
     return u < p, u
+
+
+def randint(k, minval, maxval, mode: str = LEGACY) -> np.ndarray:
+    """``jax.random.randint(key, (), minval, maxval)`` per key (jax/_src/random.py ``_randint``): two 32-bit draws from
+    ``split(key)``, combined modulo the span with the multiplier 2**32 % span (uint32 wrap-around arithmetic).  The
+    default ``integration_steps_fn`` of the dynamic kernels (rmhmc/rmhmc.py:183).  Not pinned against a JAX output
+    (none is documented): restated from the published algorithm."""
+    k = np.asarray(k, dtype=_U32)
+    ks = split(k, 2, mode)
+    hi = random_bits(ks[..., 0, :], (), mode).astype(np.uint64)
+    lo = random_bits(ks[..., 1, :], (), mode).astype(np.uint64)
+    span = np.uint64(max(int(maxval) - int(minval), 1) if maxval > minval else 1)
+    mult = np.uint64(((1 << 16) % int(span)) ** 2 % int(span))
+    m32 = np.uint64(0xFFFFFFFF)
+    off = ((((hi % span) * mult) & m32) + (lo % span)) & m32
+    return (int(minval) + (off % span).astype(np.int64)).astype(np.int32)

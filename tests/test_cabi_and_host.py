@@ -29,7 +29,7 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(N.State) == 32 and C.sizeof(N.Info) == 16 * 8
     assert C.sizeof(N.KeySource) == 8 + 8 + 5 * 8
     assert C.sizeof(N.TargetDesc) == 16 + 8 + 64 + 32
-    assert C.sizeof(N.KernelParams) == 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8
+    assert C.sizeof(N.KernelParams) == 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8  # + num_integration_steps_per_chain
 
 
 def _ar1(T, Cn, D, rho, seed):
@@ -154,3 +154,23 @@ def test_bench_data_equals_the_oracle_generator():
         X, y = make_logreg_data(N_, D_, seed)
         Xo, yo = ref(N_, D_, seed)
         assert (X == Xo).all() and (y == yo).all()
+
+
+def test_chees_host_recurrences_match_oracle():
+    """Halton jitter, Adam and dual averaging of the ChEES driver (host scalars) == the oracle's restatement."""
+    from geomjax_b200 import chees
+    from oracle import adaptation as OA, chees as OC
+    import numpy as np
+    for i in range(40):
+        assert chees.halton_sequence(i, 11) == OC.halton(i, 11)
+    opt = chees.adam(0.05)
+    st, ost = opt.init(0.3), OC.adam_init()
+    for gr in [0.5, -2.0, 1e-3, 7.0, -0.1]:
+        u, st = opt.update(gr, st, 0.0)
+        uo, ost = OC.adam_update(gr, ost, 0.05)
+        assert abs(u - uo) < 1e-15
+    da, oda = chees._da_init(0.2), OA.da_init(np.float64(0.2), np.float64)
+    for gr in [0.3, -0.2, 0.05, 0.6]:
+        da = chees._da_update(da, gr)
+        oda = OA.da_update(oda, np.float64(gr))
+        assert abs(da[0] - float(oda["log_x"])) < 1e-12 and abs(da[1] - float(oda["log_x_avg"])) < 1e-12

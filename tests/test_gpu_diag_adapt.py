@@ -127,7 +127,7 @@ def test_streaming_diagnostics_equal_batch(cuda, T_, Cn, D, rho, block):
         x[t] = rho * x[t - 1] + np.sqrt(1 - rho * rho) * rng.standard_normal((Cn, D))
     x += np.array([0.0, 100.0, -3.0, 7.0, 1e3][:D], np.float32)  # means far from zero: the shift matters
     xt = torch.from_numpy(x).to(cuda)
-    lags = 64 if T_ >= 64 else 48
+    lags = 256 if rho > 0.8 else (64 if T_ >= 64 else 48)  # enough lags for Geyer's truncation (no doubling in streaming)
     sd = g.StreamingDiagnostics(Cn, D, max_lags=lags, device=cuda)
     for t0 in range(0, T_, block):
         sd.update(xt[t0:t0 + block])

@@ -71,30 +71,35 @@ def test_c1_softabs_chain_vs_oracle_chain(cuda):
 
 
 def test_funnel_d20_lmcmonge_posterior(cuda):
-    """Neal's funnel D = 20 with lmcmonge (alpha2 restored: half_step_omega_fixed, bench/configs.json step size):
-    the posterior is known in closed form (v ~ N(0, 9), x_k | v ~ N(0, e^v)); chains mix (R-hat) and the v / x
-    moments sit within 5 MCSE of the analytic values."""
+    """Neal's funnel D = 20 with lmcmonge (alpha2 restored: half_step_omega_fixed, bench/configs.json step size).
+    The Monge metric with alpha2 = 1e-3 is nearly Euclidean, so the funnel's v coordinate decorrelates over ~2,600
+    transitions (measured: R-hat 1.04 at T = 30,000): the R-hat < 1.01 gate needs a few hundred thousand transitions
+    per chain, which only the streaming diagnostics make possible (no (T, C, D) tensor).  The posterior is known in
+    closed form (v ~ N(0, 9), x_k | v ~ N(0, e^v)): E[v] = 0, E[v^2] = 9, E[x_k] = 0 within 5 MCSE, with the MCSE
+    from the spread of the independent chains' means."""
     import torch
     import geomjax_b200 as g
-    D, C, Tn, burn = 20, 1024, 30000, 3000
+    D, C, Tn, burn = 20, 4096, 262144, 16384
     target = g.neal_funnel(D)
     alg = g.lmcmonge(target, 0.3509, torch.ones(D, device=cuda), 8, integrator=g.integrators.half_step_omega_fixed)
     st = alg.init(torch.ones((C, D), device=cuda))
-    st, _, _ = g.run_fused(alg.step, g.random.PRNGKey(3), st, burn, total=burn + Tn)
-    st, samples, acc = g.run_fused(alg.step, g.random.PRNGKey(3), st, Tn, first=burn, total=burn + Tn,
-                                   return_samples=True, return_accept="mean")
-    rhat = g.rhat(samples, chain_axis=1, sample_axis=0)
-    ess = g.ess(samples, chain_axis=1, sample_axis=0)
+    st, _, _ = g.run_fused(alg.step, g.random.PRNGKey(3), st, burn)
+    s1 = torch.zeros((C, D), dtype=torch.float64, device=cuda)
+    s2 = torch.zeros((C,), dtype=torch.float64, device=cuda)
+
+    def fold(first, blk):  # per-chain sums of x and of v^2
+        s1.add_(blk.sum(0, dtype=torch.float64))
+        s2.add_((blk[..., -1].double() ** 2).sum(0))
+
+    st, diag, acc = g.sample_streaming(alg.step, g.random.PRNGKey(4), st, Tn, block=1024, max_lags=8, on_block=fold)
+    rhat = diag.rhat()
     assert float(rhat.max()) < 1.01, rhat
-    m = samples.mean(dim=(0, 1)).cpu().numpy()
-    sd = samples.reshape(-1, D).std(0).cpu().numpy()
-    mcse = sd / np.sqrt(ess.cpu().numpy())
-    assert (np.abs(m) <= 5 * mcse).all(), (m, mcse)          # E[v] = 0, E[x_k] = 0
-    v = samples[..., -1]
-    v2 = (v * v)
-    ess_v2 = g.ess(v2.unsqueeze(-1), chain_axis=1, sample_axis=0)
-    mcse_v2 = float(v2.std()) / np.sqrt(float(ess_v2.min()))
-    assert abs(float(v2.mean()) - 9.0) <= 5 * mcse_v2, (float(v2.mean()), mcse_v2)   # Var[v] = sigma^2 = 9
+    chain_mean = (s1 / Tn).cpu().numpy()          # (C, D): independent chains
+    m = chain_mean.mean(0)
+    mcse = chain_mean.std(0, ddof=1) / np.sqrt(C)
+    assert (np.abs(m) <= 5 * mcse).all(), (m, mcse)
+    v2 = (s2 / Tn).cpu().numpy()
+    assert abs(v2.mean() - 9.0) <= 5 * v2.std(ddof=1) / np.sqrt(C), (v2.mean(), v2.std(ddof=1) / np.sqrt(C))
     assert 0.5 < float(acc.mean()) < 0.99
 
 
@@ -107,7 +112,7 @@ def test_logreg_d25_posterior_vs_oracle(cuda):
     X, y = T.make_logreg_data(N_, D, seed=0)
     target = g.logistic_regression(torch.from_numpy(X).to(cuda), torch.from_numpy(y).to(cuda), 0.01)
     alg = g.rmhmc(target, eps, target, L)
-    C, Tn, burn = 2048, 160, 24
+    C, Tn, burn = 1024, 640, 40  # trajectory length 0.6: tau ~ 10 transitions, R-hat < 1.01 needs T > 500
     st = alg.init(torch.zeros((C, D), device=cuda))
     st, samples, acc = g.run_fused(alg.step, g.random.PRNGKey(11), st, burn + Tn, return_samples=True,
                                    return_accept="mean")
@@ -125,6 +130,4 @@ def test_logreg_d25_posterior_vs_oracle(cuda):
         smp.step(S.chain_keys(P.key(5), burn + To, burn + t, Co), ost, want_info=False)
         want[t] = ost[0]
     got = x.cpu().numpy()
-    _moments_agree(got[:, :256], want, what="logreg D=25")
-    # and against the GPU's own full chain set (tighter MCSE): the 256-chain subset is representative
-    np.testing.assert_allclose(got.mean((0, 1)), got[:, :256].mean((0, 1)), atol=0.05)
+    _moments_agree(got[::4, :256], want, what="logreg D=25")
