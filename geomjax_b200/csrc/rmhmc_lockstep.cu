@@ -54,7 +54,7 @@ struct LsBuf {
   // per slot (compacted list of running chains)
   int* idx;
   unsigned char* slot_phase;
-  float *v, *logdet, *sbuf, *Gp, *Ap, *parts, *lp_parts, *dHt, *lpt;
+  float *v, *logdet, *sbuf, *Gp, *Ap, *parts, *lp_parts, *dHt, *lpt, *qT;
   // operands
   unsigned char *Wt, *Bt;
   float* Xtile;
@@ -181,59 +181,92 @@ __global__ void __launch_bounds__(1024) ls_compact_kernel(const LsBuf b, const L
   }
 }
 
+// positions of the running chains, transposed: qT[i][slot] = q[idx[slot]][i], so that the weights kernel reads them
+// coalesced over slots (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256) ls_gather_kernel(const LsBuf b, const LsDims d) {
+  __shared__ float tile[32][33];
+  const long long nact = b.n_active[0];
+  const long long j0 = (long long)blockIdx.x * 32;
+  if (j0 >= nact) return;
+  const int i0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const long long j = j0 + r;
+    const int i = i0 + tx;
+    tile[r][tx] = (j < nact && i < d.D) ? b.q[(size_t)b.idx[j] * d.D + i] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r;
+    const long long j = j0 + tx;
+    if (i < d.D && j < d.Ccap) b.qT[(size_t)i * d.Ccap + j] = tile[tx][r];
+  }
+}
+
 // eta = X q, s = sigmoid(eta), w = s(1-s) for the running chains: W operand tiles of the metric GEMM (TF32 hi / lo in
 // the UMMA canonical layout, one 32 KB block per (256-chain tile, 16-row K tile), see fisher_weights_kernel), s[slot, n],
 // and for chains at the end of their trajectory the log-density partial sums over the K tile's 16 data rows.
-__global__ void __launch_bounds__(256) ls_weights_kernel(const LsBuf b, const LsDims d) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long tile = gid >> 10;  // 1024 threads per (chain tile, K tile): 256 rows x 4 k-quads
+// One block = one (chain tile, K tile); thread = one chain, all 16 data rows of the tile: the X tile [D][16] is staged
+// in shared memory and read as warp-uniform float4 broadcasts, the positions come coalesced from qT -- 5 loads per 16
+// FMAs with no uncoalesced access (the first version, thread = (chain, 4 rows), issued 8 L2-bound loads per 16 FMAs).
+__global__ void __launch_bounds__(FT_N) ls_weights_kernel(const LsBuf b, const LsDims d) {
+  extern __shared__ __align__(16) float wsm[];  // [D][FT_KT]
   const long long nact = b.n_active[0];
   const int ktiles = d.ktF;
-  if (tile >= d.ctiles * ktiles) return;
+  const long long tile = blockIdx.x;
   const long long ct = tile / ktiles;
-  if (ct * FT_N >= nact) return;  // warp-uniform (a warp lies inside one tile)
-  const int l = (int)(gid & 1023);
-  const int rg = l >> 5, row = rg * 8 + (l & 7), kq = (l >> 3) & 3;  // a warp = one 8-row group = one chain-octet
+  if (ct * FT_N >= nact) return;
   const int kt = (int)(tile - ct * ktiles);
+  const int N = d.N, D = d.D, n0 = kt * FT_KT;
+  for (int e = threadIdx.x; e < D * (FT_KT / 4); e += FT_N) {
+    const int i = e / (FT_KT / 4), k4 = e - i * (FT_KT / 4);
+    // ldx % 4 == 0 and columns in [N, ldx) are zero; K tiles may reach beyond ldx
+    const int n = n0 + 4 * k4;
+    *(float4*)(wsm + i * FT_KT + 4 * k4) = n < d.ldx ? __ldg((const float4*)(b.Xt + (size_t)i * d.ldx + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int row = threadIdx.x;
   const long long j = ct * FT_N + row;
-  const int n = kt * FT_KT + 4 * kq;
-  const int N = d.N, D = d.D;
-  float w[4] = {0.f, 0.f, 0.f, 0.f};
-  float lp = 0.f;
   const bool live = j < nact;
   const bool end = live && b.slot_phase[j] == LS_PH_END;
-  if (live && n < N) {
-    float eta[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* th = b.q + (size_t)b.idx[j] * D;
-    const float* xp = b.Xt + n;
+  float eta[FT_KT];
+#pragma unroll
+  for (int k = 0; k < FT_KT; ++k) eta[k] = 0.f;
+  if (live) {
+    const float* th = b.qT + j;
+#pragma unroll 2
     for (int i = 0; i < D; ++i) {
-      const float4 x = __ldg((const float4*)(xp + (size_t)i * d.ldx));  // ldx % 4 == 0, columns >= N are zero
-      const float t = __ldg(th + i);
-      eta[0] = fmaf(x.x, t, eta[0]); eta[1] = fmaf(x.y, t, eta[1]);
-      eta[2] = fmaf(x.z, t, eta[2]); eta[3] = fmaf(x.w, t, eta[3]);
-    }
-    float sg[4];
+      const float t = th[(size_t)i * d.Ccap];
+      const float4* xr = (const float4*)(wsm + i * FT_KT);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      sg[e] = 1.f / (1.f + expf(-eta[e]));
-      w[e] = (n + e < N) ? sg[e] * (1.f - sg[e]) : 0.f;
-    }
-    *(float4*)(b.sbuf + (size_t)j * d.ldn + n) = make_float4(sg[0], sg[1], sg[2], sg[3]);
-    if (end) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (n + e < N) lp += __ldg(b.y + n + e) * eta[e] - (fmaxf(eta[e], 0.f) + log1pf(expf(-fabsf(eta[e]))));  // jnp.logaddexp(0, eta)
+      for (int k4 = 0; k4 < FT_KT / 4; ++k4) {
+        const float4 x = xr[k4];
+        eta[4 * k4 + 0] = fmaf(x.x, t, eta[4 * k4 + 0]);
+        eta[4 * k4 + 1] = fmaf(x.y, t, eta[4 * k4 + 1]);
+        eta[4 * k4 + 2] = fmaf(x.z, t, eta[4 * k4 + 2]);
+        eta[4 * k4 + 3] = fmaf(x.w, t, eta[4 * k4 + 3]);
+      }
     }
   }
-  // the four k-quads of a chain sit at lanes (l & 7) + 8 kq of this warp
-  lp += __shfl_xor_sync(0xffffffffu, lp, 8);
-  lp += __shfl_xor_sync(0xffffffffu, lp, 16);
-  if (end && kq == 0) b.lp_parts[(size_t)kt * d.Ccap + j] = lp;
-  float4 hi, lo;
-  ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
-  unsigned char* base = b.Wt + (size_t)tile * (2 * FT_B_BYTES) + (size_t)rg * FT_SBO + kq * FT_LBO + (l & 7) * 16;
-  *(float4*)base = hi;
-  *(float4*)(base + FT_B_BYTES) = lo;
+  float lp = 0.f;
+  unsigned char* base = b.Wt + (size_t)tile * (2 * FT_B_BYTES) + (size_t)(row >> 3) * FT_SBO + (row & 7) * 16;
+#pragma unroll
+  for (int k4 = 0; k4 < FT_KT / 4; ++k4) {
+    float sg[4], w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = n0 + 4 * k4 + e;
+      const float et = eta[4 * k4 + e];
+      sg[e] = 1.f / (1.f + expf(-et));
+      w[e] = (live && n < N) ? sg[e] * (1.f - sg[e]) : 0.f;
+      if (end && n < N) lp += __ldg(b.y + n) * et - (fmaxf(et, 0.f) + log1pf(expf(-fabsf(et))));  // jnp.logaddexp(0, eta)
+    }
+    if (live && n0 + 4 * k4 < d.ldn) *(float4*)(b.sbuf + (size_t)j * d.ldn + n0 + 4 * k4) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+    float4 hi, lo;
+    ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
+    *(float4*)(base + k4 * FT_LBO) = hi;
+    *(float4*)(base + k4 * FT_LBO + FT_B_BYTES) = lo;
+  }
+  if (end) b.lp_parts[(size_t)kt * d.Ccap + j] = lp;
 }
 
 // ---- per-chain dense algebra: blocked Cholesky / inverse with the matrix in REGISTERS ---------------------------
@@ -829,7 +862,7 @@ int64_t ls_carve(const LsDims& d, unsigned char* base, LsBuf* b) {
   t.Gp = (float*)take(C * (int64_t)d.P * 4); t.Ap = (float*)take(C * (int64_t)d.P * 4);
   t.parts = (float*)take((int64_t)d.mtQ * D * C * 4);
   t.lp_parts = (float*)take((int64_t)d.ktF * C * 4);
-  t.dHt = (float*)take(D * C * 4); t.lpt = (float*)take(C * 4);
+  t.dHt = (float*)take(D * C * 4); t.lpt = (float*)take(C * 4); t.qT = (float*)take(D * C * 4);
   t.Wt = (unsigned char*)take(d.ctiles * d.ktF * 2 * (int64_t)FT_B_BYTES);
   t.Bt = (unsigned char*)take(d.ctiles * d.ktQ * 2 * (int64_t)FT_B_BYTES);
   t.Xtile = (float*)take((int64_t)d.ktF * D * FT_XS * 4);
@@ -843,8 +876,10 @@ int ls_launch_eval(const gb200_plan* pl, cudaStream_t s) {
   const LsDims& d = pl->d;
   const LsBuf& b = pl->b;
   {
-    const long long total = d.ctiles * d.ktF * 1024;
-    ls_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(b, d);
+    dim3 gg((unsigned)((d.Ccap + 31) / 32), (unsigned)((d.D + 31) / 32));
+    ls_gather_kernel<<<gg, 256, 0, s>>>(b, d);
+    GB_CHECK_LAUNCH();
+    ls_weights_kernel<<<(unsigned)(d.ctiles * d.ktF), FT_N, sizeof(float) * d.D * FT_KT, s>>>(b, d);
     GB_CHECK_LAUNCH();
   }
   FtArgs a;
