@@ -233,17 +233,22 @@ __global__ void __launch_bounds__(FT_N) ls_weights_kernel(const LsBuf b, const L
   for (int k = 0; k < FT_KT; ++k) eta[k] = 0.f;
   if (live) {
     const float* th = b.qT + j;
-#pragma unroll 2
-    for (int i = 0; i < D; ++i) {
-      const float t = th[(size_t)i * d.Ccap];
-      const float4* xr = (const float4*)(wsm + i * FT_KT);
+    constexpr int CH = 10;  // positions are fetched CH features ahead: CH independent loads in flight per thread
+    for (int i0 = 0; i0 < D; i0 += CH) {
+      float t[CH];
 #pragma unroll
-      for (int k4 = 0; k4 < FT_KT / 4; ++k4) {
-        const float4 x = xr[k4];
-        eta[4 * k4 + 0] = fmaf(x.x, t, eta[4 * k4 + 0]);
-        eta[4 * k4 + 1] = fmaf(x.y, t, eta[4 * k4 + 1]);
-        eta[4 * k4 + 2] = fmaf(x.z, t, eta[4 * k4 + 2]);
-        eta[4 * k4 + 3] = fmaf(x.w, t, eta[4 * k4 + 3]);
+      for (int u = 0; u < CH; ++u) t[u] = (i0 + u < D) ? __ldg(th + (size_t)(i0 + u) * d.Ccap) : 0.f;
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const float4* xr = (const float4*)(wsm + min(i0 + u, D - 1) * FT_KT);
+#pragma unroll
+        for (int k4 = 0; k4 < FT_KT / 4; ++k4) {
+          const float4 x = xr[k4];
+          eta[4 * k4 + 0] = fmaf(x.x, t[u], eta[4 * k4 + 0]);
+          eta[4 * k4 + 1] = fmaf(x.y, t[u], eta[4 * k4 + 1]);
+          eta[4 * k4 + 2] = fmaf(x.z, t[u], eta[4 * k4 + 2]);
+          eta[4 * k4 + 3] = fmaf(x.w, t[u], eta[4 * k4 + 3]);
+        }
       }
     }
   }
