@@ -353,6 +353,36 @@ def ess_record(cx, alg, C, D, Tn, burnin, init_fill, thin=1):
     return rec
 
 
+def streaming_record(cx, alg, C, D, Tn, init_fill, block=32, max_lags=64):
+    """N2: Tn transitions in fused launches of `block` whose sample buffer is reused and folded into the streaming
+    R-hat / ESS accumulators -- no (T, C, D) tensor (c3 at T = 1000 would need 52 GB per GPU); statistics all-reduced
+    over ranks exactly like the batch diagnostics."""
+    g, torch = cx.g, cx.torch
+    st = alg.init(init_fill((C, D), device=cx.dev))
+    cx.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    st, diag, acc = g.sample_streaming(alg.step, cx.root, st, Tn, block=block, max_lags=max_lags, chain_offset=cx.rank * C,
+                                       total_chains=C * cx.world)
+    e1.record()
+    rhat = diag.rhat()
+    ess = diag.ess(allow_truncated=True)
+    e2.record()
+    torch.cuda.synchronize()
+    run_ms = cx.max_over_ranks(e0.elapsed_time(e1))
+    max_rhat, min_ess = float(rhat.max()), float(ess.min())
+    rec = {"samples_per_chain": Tn, "block": block, "max_lags": max_lags, "sampling_plus_update_ms": run_ms,
+           "finalize_ms": cx.max_over_ranks(e1.elapsed_time(e2)), "max_rhat": max_rhat, "min_ess": min_ess,
+           "lags_truncated_dims": int(diag.truncated.sum()), "mean_acceptance": float(acc.mean()),
+           "accumulator_bytes": int(diag._ws.numel()), "sample_tensor_bytes_avoided": int(Tn) * C * D * 4,
+           "allreduce_bytes": (3 * D + 1) * 8 + max_lags * D * 8, "min_ess_valid": bool(max_rhat < 1.01)}
+    if rec["min_ess_valid"]:
+        rec["min_ess_per_s"] = min_ess / (run_ms * 1e-3)
+    else:
+        rec["min_ess_invalid_reason"] = f"max R-hat {max_rhat:.4f} >= 1.01 after {Tn} transitions"
+    return rec
+
+
 def fp32_peak(cx):
     """FFMA issue rate of this GPU, same process, same clocks (256 FFMA per loop trip, 16 chains per thread)."""
     torch, N = cx.torch, cx.N
@@ -618,6 +648,13 @@ def run_ours(args, cfg):
                                         "accepts at eps ~ 1e-3 and therefore cannot mix in 1000 transitions.  The nearly "
                                         "Euclidean Monge metric (alpha2 = 1e-3) decorrelates the funnel's v over ~2,600 "
                                         "transitions, so this record thins by 64 to pass the R-hat gate")
+            elif s == "c3_shard":
+                c3 = CONFIGS["c3"]
+                rec = bench_funnel(cx, args, c3, "c3", TPS=64, K=5, W=3, with_e2e=False)
+                tg3 = make_target(g, torch, c3, cx.dev)
+                alg3, _, _ = make_alg(g, torch, N, c3, tg3, cx.dev)
+                rec["streaming_diagnostics"] = streaming_record(cx, alg3, c3["chains_per_gpu"], c3["D"], 1000, torch.ones)
+                workloads[s] = rec
             elif s == "c4":
                 workloads[s] = bench_logreg(cx, args, CONFIGS["c4"], C=CONFIGS["c4"]["chains_per_gpu"], T=16, K=3, W=1,
                                             label=CONFIGS["c4"]["name"], ess_samples=min(args.ess_samples, 640), burnin=40)
@@ -689,14 +726,14 @@ def main():
     ap.add_argument("--step-size", type=float, default=0.0)
     ap.add_argument("--ess-samples", type=int, default=1000)
     ap.add_argument("--ess-burnin", type=int, default=200)
-    ap.add_argument("--sub", default="default", help="comma list of sub-records (c2_omega_fixed,c4,c5_shard) or none")
+    ap.add_argument("--sub", default="default", help="comma list of sub-records (c2_omega_fixed,c3_shard,c4,c5_shard) or none")
     ap.add_argument("--no-collectives", dest="collectives", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.sub == "default":
-        args.sub = "c2_omega_fixed,c4,c5_shard" if args.workload == "c2" else "none"
+        args.sub = "c2_omega_fixed,c3_shard,c4,c5_shard" if args.workload == "c2" else "none"
     cfg = CONFIGS[args.workload]
     if args.impl == "reference":
         run_reference(args, cfg)

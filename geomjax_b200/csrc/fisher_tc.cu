@@ -187,20 +187,21 @@ fisher_metric_tc_kernel(const FtArgs a) {
   const short2* __restrict__ pairs = a.pairs;
   const int PS = a.PS, ldh = a.ldh;
   extern __shared__ __align__(1024) unsigned char ft_smem[];
-  unsigned char* Astage = ft_smem;                                  // 2 x [A_hi | A_lo]
-  unsigned char* Bslot = ft_smem + 2 * 2 * FT_A_BYTES;              // 3 x [B_hi | B_lo] (one bulk copy each)
-  float* xs0 = (float*)(ft_smem + FT_REGION);                       // 2 x [D][FT_XS] X tiles / the staged data rows
+  unsigned char* Astage = ft_smem;                                  // FT_NSA x [A_hi | A_lo]
+  unsigned char* Bslot = ft_smem + FT_NSA * 2 * FT_A_BYTES;         // FT_NSB x [B_hi | B_lo] (one bulk copy each)
+  float* xs0 = (float*)(ft_smem + FT_REGION);                       // FT_NXB x [D][FT_XS] X tiles / the staged data rows
   __shared__ uint32_t tmem_base_s;
-  // 0,1: A stage free (MMAs done); 2,3: A stage built; 4,5,6: B slot landed; 7,8: X tile landed; 9,10: accumulator complete
-  __shared__ __align__(8) unsigned long long mbar[11];
+  // mbarriers: A stage free (MMAs of its tile done) | A stage built | B slot landed | X tile landed | accumulator complete
+  constexpr int MB_FREE = 0, MB_BUILT = MB_FREE + FT_NSA, MB_BLAND = MB_BUILT + FT_NSA, MB_XLAND = MB_BLAND + FT_NSB,
+                MB_ACC = MB_XLAND + FT_NXB, MB_COUNT = MB_ACC + 2;
+  __shared__ __align__(8) unsigned long long mbar[MB_COUNT];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int P = D * (D + 1) / 2;
   const int m0 = blockIdx.x * FT_M;
   const long long ct = blockIdx.y;
   const long long c0 = ct * FT_N;
-  uint32_t mb[11];
-#pragma unroll
-  for (int i = 0; i < 11; ++i) mb[i] = (uint32_t)__cvta_generic_to_shared(&mbar[i]);
+  const uint32_t mb0 = (uint32_t)__cvta_generic_to_shared(&mbar[0]);
+  auto mb = [&](int i) { return mb0 + 8u * (uint32_t)i; };
   const uint32_t xbytes = (uint32_t)D * FT_XS * 4;
   const uint32_t bbytes = 2 * FT_B_BYTES;
   const int ktiles = QUAD ? PS / FT_KT : (N + FT_KT - 1) / FT_KT;
@@ -222,10 +223,9 @@ fisher_metric_tc_kernel(const FtArgs a) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < 11; ++i) {
-      const uint32_t cnt = (i == 2 || i == 3) ? 256u : 1u;  // "built": every producer thread arrives
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb[i]), "r"(cnt));
+    for (int i = 0; i < MB_COUNT; ++i) {
+      const uint32_t cnt = (i >= MB_BUILT && i < MB_BLAND) ? 256u : 1u;  // "built": every producer thread arrives
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb(i)), "r"(cnt));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -243,21 +243,28 @@ fisher_metric_tc_kernel(const FtArgs a) {
   };
 
   if (warp == 8) {
-    // ------------------------------------------------------------------ issuer
+    // ------------------------------------------------------------------ issuer (lane 0) and B loader (lane 1)
+    if (tid == 257) {
+      // B tile j -> slot j % FT_NSB as soon as the MMAs of tile j - FT_NSB (the slot's previous user) are done
+      for (int j = 0; j < ktiles; ++j) {
+        if (j >= FT_NSB) ft_mbar_wait(mb(MB_FREE + (j - FT_NSB) % FT_NSA), (uint32_t)(((j - FT_NSB) / FT_NSA) & 1));
+        bulk(Bslot + (size_t)(j % FT_NSB) * bbytes, Wt + ((size_t)ct * ktiles + j) * bbytes, bbytes, mb(MB_BLAND + j % FT_NSB));
+      }
+    }
     if (tid == 256) {
       if (!QUAD) {
-        bulk(xs0, Xtile, xbytes, mb[7]);
-        if (ktiles > 1) bulk(xs0 + (size_t)D * FT_XS, Xtile + (size_t)D * FT_XS, xbytes, mb[8]);
+        for (int j = 0; j < FT_NXB && j < ktiles; ++j)
+          bulk(xs0 + (size_t)j * D * FT_XS, Xtile + (size_t)j * D * FT_XS, xbytes, mb(MB_XLAND + j));
       }
-      bulk(Bslot, Wt + (size_t)ct * ktiles * bbytes, bbytes, mb[4]);
       const uint64_t dA0 = ft_smem_desc((uint32_t)__cvta_generic_to_shared(Astage));
       const uint64_t dB0 = ft_smem_desc((uint32_t)__cvta_generic_to_shared(Bslot));
       constexpr uint64_t ATILE16 = FT_A_BYTES >> 4, BTILE16 = FT_B_BYTES >> 4;  // descriptor address units are 16 bytes
       for (int j = 0; j < ktiles; ++j) {
-        const int s = j & 1, slot = j % 3;
-        ft_mbar_wait(mb[2 + s], (uint32_t)((j >> 1) & 1));   // A stage built (and X buffer s no longer read)
-        if (!QUAD && j + 2 < ktiles) bulk(xs0 + (size_t)s * D * FT_XS, Xtile + (size_t)(j + 2) * D * FT_XS, xbytes, mb[7 + s]);
-        ft_mbar_wait(mb[4 + slot], (uint32_t)((j / 3) & 1));  // B slot landed
+        const int s = j % FT_NSA, slot = j % FT_NSB;
+        ft_mbar_wait(mb(MB_BUILT + s), (uint32_t)((j / FT_NSA) & 1));   // A stage built (and X buffer j % FT_NXB no longer read)
+        if (!QUAD && j + FT_NXB < ktiles)
+          bulk(xs0 + (size_t)(j % FT_NXB) * D * FT_XS, Xtile + (size_t)(j + FT_NXB) * D * FT_XS, xbytes, mb(MB_XLAND + j % FT_NXB));
+        ft_mbar_wait(mb(MB_BLAND + slot), (uint32_t)((j / FT_NSB) & 1));  // B slot landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t a_hi = dA0 + (uint64_t)s * 2 * ATILE16, a_lo = a_hi + ATILE16;
         const uint64_t b_hi = dB0 + (uint64_t)slot * 2 * BTILE16, b_lo = b_hi + BTILE16;
@@ -272,9 +279,9 @@ fisher_metric_tc_kernel(const FtArgs a) {
           ft_mma(td, a_lo + adv, b_hi + adv, 1u);
         }
         // arrive when every MMA issued so far has finished reading shared memory / writing TMEM
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb[s]) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb(MB_FREE + s)) : "memory");
         if ((j % FT_KC) == FT_KC - 1 || j == ktiles - 1)
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb[9 + (chunk & 1)]) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb(MB_ACC + (chunk & 1))) : "memory");
       }
     }
   } else {
@@ -303,7 +310,7 @@ fisher_metric_tc_kernel(const FtArgs a) {
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;  // warp w may access TMEM lanes 32 (w % 4) ..
 
     auto drain = [&](int chunk) {  // accumulator (chunk & 1) -> registers
-      ft_mbar_wait(mb[9 + (chunk & 1)], (uint32_t)((chunk >> 1) & 1));
+      ft_mbar_wait(mb(MB_ACC + (chunk & 1)), (uint32_t)((chunk >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t col0 = (uint32_t)((chunk & 1) * FT_N + half * NH);
 #pragma unroll
@@ -325,14 +332,13 @@ fisher_metric_tc_kernel(const FtArgs a) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     };
 
+    int drained = 0;  // chunks already added to acc[]
     for (int kt = 0; kt < ktiles; ++kt) {
-      const int s = kt & 1, use = kt >> 1;
-      const float* xs = xs0 + (size_t)s * D * FT_XS;
+      const int s = kt % FT_NSA, use = kt / FT_NSA;
+      const float* xs = xs0 + (size_t)(kt % FT_NXB) * D * FT_XS;
       unsigned char* A_hi = Astage + (size_t)s * 2 * FT_A_BYTES;
       unsigned char* A_lo = A_hi + FT_A_BYTES;
-      if (kt >= 2) ft_mbar_wait(mb[s], (uint32_t)((use - 1) & 1));  // MMAs of tile kt - 2 done: A stage s, B slot (kt+1)%3 free
-      if (tid == 0 && kt + 1 < ktiles)
-        bulk(Bslot + (size_t)((kt + 1) % 3) * bbytes, Wt + ((size_t)ct * ktiles + kt + 1) * bbytes, bbytes, mb[4 + (kt + 1) % 3]);
+      if (kt >= FT_NSA) ft_mbar_wait(mb(MB_FREE + s), (uint32_t)((use - 1) & 1));  // MMAs of tile kt - FT_NSA done: A stage s is free
       if (QUAD) {
         // A stage: row = data row, z = x_i x_j over the 32 pairs of this K tile (pair list is warp-uniform)
         const float* xrow = xs0 + row * DX;
@@ -353,7 +359,7 @@ fisher_metric_tc_kernel(const FtArgs a) {
           *(float4*)(A_lo + off) = lo;
         }
       } else {
-      ft_mbar_wait(mb[7 + s], (uint32_t)(use & 1));  // X tile kt landed
+      ft_mbar_wait(mb(MB_XLAND + kt % FT_NXB), (uint32_t)((kt / FT_NXB) & 1));  // X tile kt landed
       {
         const float* xi = xs + (pi >= 0 ? pi : 0) * FT_XS;
         const float* xj = xs + (pi >= 0 ? pj : 0) * FT_XS;
@@ -375,13 +381,16 @@ fisher_metric_tc_kernel(const FtArgs a) {
       }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb[2 + s]) : "memory");
-      // the first tile of a new chunk is queued: drain the previous chunk's accumulator under it.  This thread
-      // arrives for a later tile only after its drain, and the accumulator's next overwrite is issued FT_KC
-      // tiles later, after every producer arrived for that tile.
-      if ((kt % FT_KC) == 0 && kt > 0) drain(kt / FT_KC - 1);
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb(MB_BUILT + s)) : "memory");
+      // FT_DRAIN_LAG tiles of a new chunk are queued: drain the previous chunk's accumulator under them.  This thread
+      // arrives for a later tile only after its drain, and that accumulator's next overwrite (first tile of the chunk
+      // after next, FT_KC > FT_DRAIN_LAG tiles later) is issued only after every producer arrived for that tile.
+      if (kt >= FT_KC && (kt % FT_KC) == FT_DRAIN_LAG) {
+        drain(kt / FT_KC - 1);
+        drained = kt / FT_KC;
+      }
     }
-    drain(nchunks - 1);
+    for (int c = drained; c < nchunks; ++c) drain(c);
 
     if (QUAD && EPI == 1) {
       // every MMA has completed (the last accumulator is drained): the operand stages are free and hold R now

@@ -18,7 +18,11 @@ constexpr int FT_LBO = 128;                  // bytes
 constexpr int FT_SBO = (FT_KT / 4) * 128;    // bytes
 constexpr int FT_A_BYTES = FT_M * FT_KT * 4;  // one A tile (hi or lo)
 constexpr int FT_B_BYTES = FT_N * FT_KT * 4;  // one B tile (hi or lo)
-constexpr int FT_STAGE_REGION = 2 * 2 * FT_A_BYTES + 3 * 2 * FT_B_BYTES;  // 2 A stages + 3 B slots (hi + lo each)
+constexpr int FT_NSA = 4;      // A stages in flight (ring): the producers run up to 4 K tiles ahead of the tensor core
+constexpr int FT_NSB = 3;      // B slots (one bulk-TMA copy each, issued by a dedicated lane)
+constexpr int FT_NXB = 4;      // X tile buffers of the metric GEMM (bulk-copied 4 K tiles ahead)
+constexpr int FT_DRAIN_LAG = 2;  // a finished TMEM chunk is drained after the producers queued this many tiles of the next
+constexpr int FT_STAGE_REGION = FT_NSA * 2 * FT_A_BYTES + FT_NSB * 2 * FT_B_BYTES;  // A ring + B slots (hi + lo each)
 constexpr int FT_EPI_REGION = FT_N * 129 * 4;                             // R[chain][129] of the fused epilogue
 constexpr int FT_REGION = ((FT_STAGE_REGION > FT_EPI_REGION ? FT_STAGE_REGION : FT_EPI_REGION) + 1023) / 1024 * 1024;
 
@@ -62,7 +66,7 @@ int ft_launch_quad_b_packed(const float* Ap, int D, long long C, const int* n_ac
                             cudaStream_t s);
 int ft_set_attributes(int D);  // cudaFuncSetAttribute for both GEMM kernels (outside stream capture)
 inline int ft_ps(int D) { const int P = D * (D + 1) / 2; return (P + FT_KT - 1) / FT_KT * FT_KT; }
-inline size_t ft_metric_smem(int D) { return (size_t)FT_REGION + 2 * (size_t)D * FT_XS * 4 + 1024; }
+inline size_t ft_metric_smem(int D) { return (size_t)FT_REGION + FT_NXB * (size_t)D * FT_XS * 4 + 1024; }
 inline size_t ft_quad_smem(int D) { return (size_t)FT_REGION + (size_t)FT_M * (D | 1) * 4 + 1024; }
 
 }  // namespace gb

@@ -31,7 +31,7 @@
 namespace gb {
 
 struct LsDims {
-  int N, D, ldx, ldn, P, PS, ktF, ktQ, mtQ, BS, NB, nblk, fthreads;
+  int N, D, ldx, ldn, P, PS, ktF, ktQ, mtQ, BS, NB, nblk, fthreads, fwarp, fsmem_floats;
   long long Ccap, ctiles;
   float alpha;
 };
@@ -285,15 +285,20 @@ __global__ void __launch_bounds__(FT_N) ls_weights_kernel(const LsBuf b, const L
 // :120-127 (v = G^-1 p).
 __device__ __forceinline__ int ls_blk(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
 
-template <int BS>
-__global__ void __launch_bounds__(BS == 8 ? 160 : 64) ls_factor_kernel(const LsBuf b, const LsDims d) {
-  extern __shared__ __align__(16) float fsm[];
-  const long long j = blockIdx.x;
-  if (j >= b.n_active[0]) return;
+// WARP: the block triangle fits one warp (nblk <= 32, i.e. D <= 28 with BS = 4): one WARP per chain, four chains per
+// CTA, __syncwarp instead of CTA barriers (c4: D = 25 used 28 of a 64-thread CTA's lanes with 20 CTA barriers).
+template <int BS, bool WARP>
+__global__ void __launch_bounds__(BS == 8 ? 160 : 128) ls_factor_kernel(const LsBuf b, const LsDims d) {
+  extern __shared__ __align__(16) float fsm_all[];
+  const long long j = WARP ? (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : (long long)blockIdx.x;
+  if (j >= b.n_active[0]) return;  // whole warp / whole CTA
   const int c = b.idx[j];
   const int ph = b.slot_phase[j];
-  const int D = d.D, NB = d.NB, nblk = d.nblk, tid = threadIdx.x, nthr = blockDim.x;
+  const int D = d.D, NB = d.NB, nblk = d.nblk;
+  const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x, nthr = WARP ? 32 : (int)blockDim.x;
   constexpr int ST = BS * BS + 4;
+  float* fsm = fsm_all + (WARP ? (size_t)(threadIdx.x >> 5) * d.fsmem_floats : 0);
+  auto sync = [&]() { if (WARP) __syncwarp(); else __syncthreads(); };
   float* Ls = fsm;               // [nblk][ST] L blocks, k-major: Ls[blk][k BS + a] = L[BS bi + a][BS bj + k]
   float* Li = Ls + nblk * ST;    // [nblk][ST] L^-1 blocks, row-major
   float* Dv = Li + nblk * ST;    // [NB][ST]   inverses of the diagonal blocks of L, row-major
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(BS == 8 ? 160 : 64) ls_factor_kernel(const LsB
       }
       logd[kb] = ld;
     }
-    __syncthreads();
+    sync();
     if (has && bj == kb && bi > kb) {  // panel: A <- A L_kk^-T, in place (descending column index)
       const float* W = Dv + kb * ST;
 #pragma unroll
@@ -394,7 +399,7 @@ __global__ void __launch_bounds__(BS == 8 ? 160 : 64) ls_factor_kernel(const LsB
 #pragma unroll
         for (int a_ = 0; a_ < BS; ++a_) lo[k * BS + a_] = A[a_][k];
     }
-    __syncthreads();
+    sync();
     if (has && bj > kb) {  // trailing update: A -= L[bi][kb] L[bj][kb]^T
       const float* La = Ls + ls_blk(bi, kb) * ST;
       const float* Lb = Ls + ls_blk(bj, kb) * ST;
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(BS == 8 ? 160 : 64) ls_factor_kernel(const LsB
       }
     }
   }
-  __syncthreads();
+  sync();
 
   // ---- momentum draw p = L z (rmhmc/metrics.py:45-58) at the first evaluation of a transition
   if (ph == LS_PH_FIRST0) {
@@ -426,7 +431,7 @@ __global__ void __launch_bounds__(BS == 8 ? 160 : 64) ls_factor_kernel(const LsB
       }
       vs[i] = s;
     }
-    __syncthreads();
+    sync();
     for (int i = tid; i < D; i += nthr) {
       const float pv = vs[i];
       ps[i] = pv;
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(BS == 8 ? 160 : 64) ls_factor_kernel(const LsB
       b.pi[(size_t)c * D + i] = pv;
       b.p0[(size_t)c * D + i] = pv;
     }
-    __syncthreads();
+    sync();
   }
 
   // ---- L^-1 by block forward substitution (A is reused as the accumulator S)
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(BS == 8 ? 160 : 64) ls_factor_kernel(const LsB
 #pragma unroll
     for (int e = 0; e < BS * BS; e += 4) *(float4*)(li + e) = *(const float4*)(dv + e);
   }
-  __syncthreads();
+  sync();
   for (int m = 0; m < NB - 1; ++m) {
     if (has && bi - bj > m) {
       const int kb = bj + m;
@@ -489,7 +494,7 @@ __global__ void __launch_bounds__(BS == 8 ? 160 : 64) ls_factor_kernel(const LsB
           for (int b_ = 0; b_ < BS; ++b_) li[a_ * BS + b_] = A[a_][b_];
       }
     }
-    __syncthreads();
+    sync();
   }
 
   // ---- G^-1 = L^-T L^-1, block (bi, bj) = sum_{kb >= bi} Li[kb][bi]^T Li[kb][bj]
@@ -521,7 +526,7 @@ __global__ void __launch_bounds__(BS == 8 ? 160 : 64) ls_factor_kernel(const LsB
 #pragma unroll
       for (int b_ = 0; b_ < BS; ++b_) gs[a_ * BS + b_] = A[a_][b_];
   }
-  __syncthreads();
+  sync();
 
   // ---- v = G^-1 p (rmhmc/metrics.py:120-127), thread = row
   for (int i = tid; i < D; i += nthr) {
@@ -538,7 +543,7 @@ __global__ void __launch_bounds__(BS == 8 ? 160 : 64) ls_factor_kernel(const LsB
     b.v[(size_t)j * D + i] = s;
   }
   for (int i = D + tid; i < DP; i += nthr) vs[i] = 0.f;
-  __syncthreads();
+  sync();
 
   // ---- A' = G^-1 - v v^T, packed pairs with the off-diagonal factor 2: x^T A' x = h - u^2 (u = x . v)
   if (has) {
@@ -831,16 +836,18 @@ int ls_dims(const gb200_target_desc* t, int64_t C, LsDims* d) {
   d->nblk = d->NB * (d->NB + 1) / 2;
   const int need = d->nblk > d->D ? d->nblk : d->D;
   d->fthreads = (need + 31) / 32 * 32;
+  d->fwarp = (d->BS == 4 && d->nblk <= 32 && d->D <= 32) ? 1 : 0;  // one warp per chain, 4 chains per CTA
+  {
+    const int ST = d->BS * d->BS + 4;
+    d->fsmem_floats = ((2 * d->nblk + d->NB) * ST + 2 * d->NB * d->BS + d->NB + 8 + 3) / 4 * 4;
+  }
   d->Ccap = C;
   d->ctiles = (C + FT_N - 1) / FT_N;
   d->alpha = (float)t->params[0];
   return GB200_OK;
 }
 
-size_t ls_factor_smem(const LsDims& d) {
-  const int ST = d.BS * d.BS + 4;
-  return sizeof(float) * ((size_t)(2 * d.nblk + d.NB) * ST + 2 * d.NB * d.BS + d.NB + 8);
-}
+size_t ls_factor_smem(const LsDims& d) { return sizeof(float) * (size_t)d.fsmem_floats * (d.fwarp ? 4 : 1); }
 
 // carve the workspace; with base == NULL only the size is computed
 int64_t ls_carve(const LsDims& d, unsigned char* base, LsBuf* b) {
@@ -893,8 +900,9 @@ int ls_launch_eval(const gb200_plan* pl, cudaStream_t s) {
   a.out = b.Gp; a.packed = 1;
   int rc = ft_launch_metric_gemm(a, d.ctiles, s);
   if (rc) return rc;
-  if (d.BS == 8) ls_factor_kernel<8><<<(unsigned)d.Ccap, d.fthreads, ls_factor_smem(d), s>>>(b, d);
-  else ls_factor_kernel<4><<<(unsigned)d.Ccap, d.fthreads, ls_factor_smem(d), s>>>(b, d);
+  if (d.BS == 8) ls_factor_kernel<8, false><<<(unsigned)d.Ccap, d.fthreads, ls_factor_smem(d), s>>>(b, d);
+  else if (d.fwarp) ls_factor_kernel<4, true><<<(unsigned)((d.Ccap + 3) / 4), 128, ls_factor_smem(d), s>>>(b, d);
+  else ls_factor_kernel<4, false><<<(unsigned)d.Ccap, d.fthreads, ls_factor_smem(d), s>>>(b, d);
   GB_CHECK_LAUNCH();
   rc = ft_launch_quad_b_packed(b.Ap, d.D, d.Ccap, b.n_active, b.Bt, d.ctiles, s);
   if (rc) return rc;
@@ -1064,8 +1072,9 @@ int gb200_rmhmc_logreg_plan_create(const gb200_target_desc* t, int64_t C, void* 
   cudaGetDevice(&pl->device);
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
-  if (d.BS == 8) e = cudaFuncSetAttribute(ls_factor_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
-  else e = cudaFuncSetAttribute(ls_factor_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
+  if (d.BS == 8) e = cudaFuncSetAttribute(ls_factor_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
+  else if (d.fwarp) e = cudaFuncSetAttribute(ls_factor_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
+  else e = cudaFuncSetAttribute(ls_factor_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
   if (e != cudaSuccess) { set_error("plan_create: %s", cudaGetErrorString(e)); delete pl; return GB200_ERR_CUDA; }
   rc = ft_set_attributes(d.D);
   if (rc == GB200_OK) rc = ft_launch_xtile(pl->b.Xt, d.ldx, d.N, d.D, pl->b.Xtile, s);
