@@ -69,7 +69,10 @@ __global__ void __launch_bounds__(256) k_ess_partial(const R* __restrict__ x, lo
   for (long long i = threadIdx.x; i < (long long)ns * T; i += blockDim.x) {
     const int s = (int)(i % ns);
     const long long t = i / ns;
-    xs[(long long)s * TS + t] = (float)x[t * CD + (c0 + s) * D + d];
+    // shifted by the series' first sample IN THE SOURCE PRECISION before the cast (float64 inputs, or means much
+    // larger than the spread, would otherwise lose their low bits here); the per-series mean is removed below
+    const long long sd = (c0 + s) * D + d;
+    xs[(long long)s * TS + t] = (float)(x[t * CD + sd] - x[sd]);
   }
   __syncthreads();
   // centre each series on its own mean (diagnostics.py:122-124)

@@ -4,6 +4,10 @@ computed on the GPU as chain-summed sufficient statistics and finalised on the h
 When the chain axis is sharded over ranks (one process per GPU), pass ``process_group`` (or
 rely on the default group): the statistics are plain sums over chains, so ONE all-reduce(sum)
 of 3D+1 (R-hat) / num_lags*D (ESS) float64 values gives every rank the global answer.
+
+The results are O(D) host-finalised values and are returned as CPU tensors (the reference returns device arrays);
+call ``.to(device)`` to combine them with CUDA tensors.  The batch ``ess`` holds a whole series in shared memory
+(T <= ~51k samples); longer runs go through ``StreamingDiagnostics`` / ``sample_streaming`` below.
 """
 from __future__ import annotations
 
