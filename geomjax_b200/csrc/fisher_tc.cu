@@ -345,13 +345,13 @@ fisher_metric_tc_kernel(const FtArgs a) {
 #pragma unroll
         for (int kq = 0; kq < FT_KT / 8; ++kq) {
           const int k4 = half * (FT_KT / 8) + kq;
-          const short2* pp = pairs + kt * FT_KT + 4 * k4;
+          // four (i, j) pairs = one 16-byte load (warp-uniform address)
+          const uint4 pq = __ldg((const uint4*)(pairs + kt * FT_KT + 4 * k4));
+          const unsigned int pw[4] = {pq.x, pq.y, pq.z, pq.w};
           float z[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const short2 ij = __ldg(pp + e);
-            z[e] = xrow[ij.x] * xrow[ij.y];  // padded pairs point at (0, 0) and meet zero rows of B
-          }
+          for (int e = 0; e < 4; ++e)  // padded pairs point at (0, 0) and meet zero rows of B
+            z[e] = xrow[pw[e] & 0xffffu] * xrow[pw[e] >> 16];
           float4 hi, lo;
           ft_split(z[0], hi.x, lo.x); ft_split(z[1], hi.y, lo.y); ft_split(z[2], hi.z, lo.z); ft_split(z[3], hi.w, lo.w);
           const int off = (row >> 3) * FT_SBO + k4 * FT_LBO + (row & 7) * 16;
@@ -397,16 +397,33 @@ fisher_metric_tc_kernel(const FtArgs a) {
       float* Rs = (float*)ft_smem;  // [256 chains][129]: conflict-free for lanes = rows (write) and lanes = chains (read)
       const int n = m0 + row;
       const float yn = (n < N) ? __ldg(a.y + n) : 0.f;
+      // s and the phase come from global memory: fetched 8 chains ahead with explicit read-only loads.  (Written
+      // as load-use-store per chain, the compiler could not move a generic-pointer load across the shared-memory
+      // store of the previous chain: 128 serialised ~1,000-cycle loads = 55 us per CTA, 70 % of this kernel's time
+      // at c4's shape.)
+      constexpr int EB = 8;
 #pragma unroll
-      for (int e = 0; e < NH; ++e) {  // fully unrolled: acc[] must keep static register indices
-        const long long j = c0 + half * NH + e;
-        float R = 0.f;
-        if (j < C && n < N) {
-          const float s = a.sbuf[(size_t)j * a.lds + n];
-          const float t = s * (1.f - s) * (1.f - 2.f * s) * acc[e];
-          R = (a.slot_phase[j] == LS_PH_END ? 0.f : 0.5f * t) - (yn - s);
+      for (int e0 = 0; e0 < NH; e0 += EB) {  // fully unrolled: acc[] must keep static register indices
+        float sv[EB];
+        unsigned int endv = 0;
+#pragma unroll
+        for (int u = 0; u < EB; ++u) {
+          const long long j = c0 + half * NH + e0 + u;
+          const bool live = j < C && n < N;
+          sv[u] = live ? __ldg(a.sbuf + (size_t)j * a.lds + n) : 0.f;
+          if (j < C && __ldg(a.slot_phase + j) == LS_PH_END) endv |= 1u << u;
         }
-        Rs[(half * NH + e) * 129 + row] = R;
+#pragma unroll
+        for (int u = 0; u < EB; ++u) {
+          const long long j = c0 + half * NH + e0 + u;
+          float R = 0.f;
+          if (j < C && n < N) {
+            const float sg = sv[u];
+            const float t = sg * (1.f - sg) * (1.f - 2.f * sg) * acc[e0 + u];
+            R = ((endv >> u) & 1u ? 0.f : 0.5f * t) - (yn - sg);
+          }
+          Rs[(half * NH + e0 + u) * 129 + row] = R;
+        }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 producer warps (the issuer warp is not involved)
       // parts[m tile][i][c] = sum_r x[r, i] R[r, c]: a 128 x D x 128 product on the FP32 pipe, register-tiled

@@ -141,8 +141,12 @@ __device__ __forceinline__ void monge_draw(const LAY& lay, R a2, MongeVecs<R, LA
 // fused multi-transition launches of a sampling run): all of that code is compiled out.  Both exist
 // because the kernel is instruction-cache bound (ncu: 35% of stall samples are no_instruction when
 // the hot code exceeds the 32 KB L1.5 I-cache).
+// Register cap for the small float layouts (EPL <= 10: c2's (10, 2)): 5 blocks of 128 threads per SM = 96 registers
+// (127 uncapped, no spills at 96): 20 instead of 16 resident warps per SM for c2's 27.7 warps per SM.  Measured: no
+// change (65.6 vs 65.9 ms per 2048-transition launch) -- the kernel is issue-bound, not occupancy-bound; the same cap
+// on lmc's (25, 4) layout changed nothing either (c3: 5.84e9 vs 5.88e9) and was not kept.
 template <typename R, class Target, int EPL, int LPC, bool EXACT, bool UNIT, int HS = -1, bool LEAN = false>
-__global__ void __launch_bounds__(128) lmcmonge_kernel(const TransArgs a, const Target tg) {
+__global__ void __launch_bounds__(128, (sizeof(R) == 4 && EPL <= 10) ? 5 : 1) lmcmonge_kernel(const TransArgs a, const Target tg) {
   using LAY = Lay<EPL, LPC, EXACT>;
   const int half_step = HS >= 0 ? HS : a.half_step;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;

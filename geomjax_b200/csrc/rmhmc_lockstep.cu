@@ -335,11 +335,15 @@ __global__ void __launch_bounds__(BS == 8 ? 160 : 128) ls_factor_kernel(const Ls
   // ---- Cholesky
   for (int kb = 0; kb < NB; ++kb) {
     if (has && bi == kb && bj == kb) {
+      // this thread works alone while the rest of the chain's threads wait at the barrier: one reciprocal per
+      // pivot (no divisions below), and ONE logarithm per block (of the product of its pivots)
+      float rd[BS];
 #pragma unroll
       for (int k = 0; k < BS; ++k) {
         const float dk = sqrtf(A[k][k]);
         A[k][k] = dk;
         const float rk = 1.f / dk;
+        rd[k] = rk;
 #pragma unroll
         for (int a_ = k + 1; a_ < BS; ++a_) A[a_][k] *= rk;
 #pragma unroll
@@ -354,18 +358,18 @@ __global__ void __launch_bounds__(BS == 8 ? 160 : 128) ls_factor_kernel(const Ls
         for (int b_ = 0; b_ < BS; ++b_) W[a_][b_] = 0.f;
 #pragma unroll
       for (int cc = 0; cc < BS; ++cc) {
-        W[cc][cc] = 1.f / A[cc][cc];
+        W[cc][cc] = rd[cc];
 #pragma unroll
         for (int r = cc + 1; r < BS; ++r) {
           float s = 0.f;
 #pragma unroll
           for (int k = cc; k < r; ++k) s = fmaf(A[r][k], W[k][cc], s);
-          W[r][cc] = -s / A[r][r];
+          W[r][cc] = -s * rd[r];
         }
       }
       float* lo = Ls + ls_blk(kb, kb) * ST;
       float* dv = Dv + kb * ST;
-      float ld = 0.f;
+      float pr0 = 1.f, pr1 = 1.f;  // pivots of the first / second half of the block (two products: no overflow for |pivot| < 1e9)
 #pragma unroll
       for (int a_ = 0; a_ < BS; ++a_) {
 #pragma unroll
@@ -373,9 +377,11 @@ __global__ void __launch_bounds__(BS == 8 ? 160 : 128) ls_factor_kernel(const Ls
           lo[k * BS + a_] = (k <= a_) ? A[a_][k] : 0.f;
           dv[a_ * BS + k] = W[a_][k];
         }
-        if (BS * kb + a_ < D) ld += logf(A[a_][a_]);
+        if (BS * kb + a_ < D) {
+          if (a_ < BS / 2) pr0 *= A[a_][a_]; else pr1 *= A[a_][a_];
+        }
       }
-      logd[kb] = ld;
+      logd[kb] = logf(pr0) + logf(pr1);
     }
     sync();
     if (has && bj == kb && bi > kb) {  // panel: A <- A L_kk^-T, in place (descending column index)
