@@ -207,6 +207,16 @@ fisher_metric_tc_kernel(const FtArgs a) {
   const int ktiles = QUAD ? PS / FT_KT : (N + FT_KT - 1) / FT_KT;
   const int nchunks = (ktiles + FT_KC - 1) / FT_KC;
   const int DX = D | 1;  // QUAD: odd row stride of the staged data rows xr[128][DX] (lanes = rows: conflict-free)
+  if (QUAD && EPI == 1) {
+    // the fused epilogue reads s[chain, row] for this CTA's 256 chains x 128 rows (512 contiguous bytes per chain):
+    // ask for those lines now, so that they wait in L2 when the main loop is done (from HBM the epilogue's loads
+    // were 50 % of the kernel's stall samples at c4's shape)
+    for (int e = tid; e < FT_N * 4; e += FT_THREADS) {
+      const long long j = c0 + (e >> 2);
+      const int n = m0 + (e & 3) * 32;
+      if (j < C && n < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.sbuf + (size_t)j * a.lds + n));
+    }
+  }
   if (QUAD) {
     float* xr = xs0;
     for (int e = tid; e < FT_M * D; e += FT_THREADS) {
