@@ -176,9 +176,14 @@ __global__ void __launch_bounds__(128) lmc_kernel(const TransArgs a, const Targe
     const R l0 = ((const R*)slogp)[chain];
     const R J0 = ((const R*)svol)[chain];
 
-    U2 key = transition_key(a, chain, t);
     U2 k_v, k_a;
-    split2(LEAN ? GB200_THREEFRY_LEGACY : a.mode, key, k_v, k_a);
+    if (LEAN && LPC >= 2) {  // lean = legacy threefry: the two lanes of a pair share the key-tree blocks
+      const U2 key = transition_key_shared(a, chain, t, lay.g);
+      split2_shared(key, lay.g, k_v, k_a);
+    } else {
+      const U2 key = transition_key(a, chain, t);
+      split2(LEAN ? GB200_THREEFRY_LEGACY : a.mode, key, k_v, k_a);
+    }
     typename Target::Ctx ctx = tg.prepare(lay, q);
     {
       R z[EPL];

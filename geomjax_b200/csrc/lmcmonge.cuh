@@ -210,9 +210,14 @@ __global__ void __launch_bounds__(128, (sizeof(R) == 4 && EPL <= 10) ? 5 : 1) lm
       m.dl[k] *= rs;
       if (!UNIT) m.dl_ig_[UNIT ? 0 : k] = m.im(k) * m.dl[k];
     }
-    U2 key = transition_key(a, chain, t);
     U2 k_v, k_a;
-    split2(LEAN ? GB200_THREEFRY_LEGACY : a.mode, key, k_v, k_a);
+    if (LEAN && LPC >= 2) {  // lean = legacy threefry: the two lanes of a pair share the key-tree blocks
+      const U2 key = transition_key_shared(a, chain, t, lay.g);
+      split2_shared(key, lay.g, k_v, k_a);
+    } else {
+      const U2 key = transition_key(a, chain, t);
+      split2(LEAN ? GB200_THREEFRY_LEGACY : a.mode, key, k_v, k_a);
+    }
     {
       R z[EPL];
       draw_noise<R, LAY, LEAN>(a, lay, k_v, chain, z);

@@ -137,10 +137,18 @@ __global__ void __launch_bounds__(1024) ls_compact_kernel(const LsBuf b, const L
   __shared__ int wsum[32];
   __shared__ int total_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long per = (d.Ccap + 1023) / 1024;
+  // each thread owns a contiguous run of chains, a multiple of 16 long: phases are read 16 at a time (one 16-byte
+  // load; the phase array is 256-byte aligned and padded, lanes beyond Ccap are masked)
+  const long long per = ((d.Ccap + 1023) / 1024 + 15) / 16 * 16;
   const long long lo = (long long)tid * per, hi = lo + per < d.Ccap ? lo + per : d.Ccap;
   int cnt = 0;
-  for (long long c = lo; c < hi; ++c) cnt += b.phase[c] != LS_PH_DONE;
+  for (long long c = lo; c < hi; c += 16) {
+    const uint4 v = *(const uint4*)(b.phase + c);
+    const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      cnt += (c + k < hi) && ((w[k >> 2] >> (8 * (k & 3))) & 0xffu) != LS_PH_DONE;
+  }
   int inc = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -161,12 +169,17 @@ __global__ void __launch_bounds__(1024) ls_compact_kernel(const LsBuf b, const L
   }
   __syncthreads();
   int pos = wsum[warp] + inc - cnt;
-  for (long long c = lo; c < hi; ++c) {
-    const unsigned char ph = b.phase[c];
-    if (ph != LS_PH_DONE) {
-      b.idx[pos] = (int)c;
-      b.slot_phase[pos] = ph;
-      ++pos;
+  for (long long c = lo; c < hi; c += 16) {
+    const uint4 v = *(const uint4*)(b.phase + c);
+    const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const unsigned char ph = (unsigned char)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+      if (c + k < hi && ph != LS_PH_DONE) {
+        b.idx[pos] = (int)(c + k);
+        b.slot_phase[pos] = ph;
+        ++pos;
+      }
     }
   }
   if (tid == 0) {
@@ -287,8 +300,10 @@ __device__ __forceinline__ int ls_blk(int bi, int bj) { return bi * (bi + 1) / 2
 
 // WARP: the block triangle fits one warp (nblk <= 32, i.e. D <= 28 with BS = 4): one WARP per chain, four chains per
 // CTA, __syncwarp instead of CTA barriers (c4: D = 25 used 28 of a 64-thread CTA's lanes with 20 CTA barriers).
-template <int BS, bool WARP>
-__global__ void __launch_bounds__(BS == 8 ? 160 : 128) ls_factor_kernel(const LsBuf b, const LsDims d) {
+// MAXT / MINB: D <= 120 with BS = 8 needs at most 128 threads; capping the registers at 128 (four CTAs per SM, what
+// shared memory allows at D = 100) instead of the 129 the compiler picks raises the residency from 3 to 4 chains per SM.
+template <int BS, bool WARP, int MAXT = (BS == 8 ? 160 : 128), int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB) ls_factor_kernel(const LsBuf b, const LsDims d) {
   extern __shared__ __align__(16) float fsm_all[];
   const long long j = WARP ? (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : (long long)blockIdx.x;
   if (j >= b.n_active[0]) return;  // whole warp / whole CTA
@@ -906,7 +921,8 @@ int ls_launch_eval(const gb200_plan* pl, cudaStream_t s) {
   a.out = b.Gp; a.packed = 1;
   int rc = ft_launch_metric_gemm(a, d.ctiles, s);
   if (rc) return rc;
-  if (d.BS == 8) ls_factor_kernel<8, false><<<(unsigned)d.Ccap, d.fthreads, ls_factor_smem(d), s>>>(b, d);
+  if (d.BS == 8 && d.fthreads <= 128) ls_factor_kernel<8, false, 128, 4><<<(unsigned)d.Ccap, d.fthreads, ls_factor_smem(d), s>>>(b, d);
+  else if (d.BS == 8) ls_factor_kernel<8, false><<<(unsigned)d.Ccap, d.fthreads, ls_factor_smem(d), s>>>(b, d);
   else if (d.fwarp) ls_factor_kernel<4, true><<<(unsigned)((d.Ccap + 3) / 4), 128, ls_factor_smem(d), s>>>(b, d);
   else ls_factor_kernel<4, false><<<(unsigned)d.Ccap, d.fthreads, ls_factor_smem(d), s>>>(b, d);
   GB_CHECK_LAUNCH();
@@ -1078,7 +1094,8 @@ int gb200_rmhmc_logreg_plan_create(const gb200_target_desc* t, int64_t C, void* 
   cudaGetDevice(&pl->device);
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
-  if (d.BS == 8) e = cudaFuncSetAttribute(ls_factor_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
+  if (d.BS == 8 && d.fthreads <= 128) e = cudaFuncSetAttribute(ls_factor_kernel<8, false, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
+  else if (d.BS == 8) e = cudaFuncSetAttribute(ls_factor_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
   else if (d.fwarp) e = cudaFuncSetAttribute(ls_factor_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
   else e = cudaFuncSetAttribute(ls_factor_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
   if (e != cudaSuccess) { set_error("plan_create: %s", cudaGetErrorString(e)); delete pl; return GB200_ERR_CUDA; }

@@ -45,6 +45,31 @@ __device__ __forceinline__ U2 transition_key(const TransArgs& a, long long chain
                    (uint32_t)a.ks.total_chains, (uint32_t)(a.ks.chain_offset + chain));
 }
 
+// Lean launches (legacy threefry) with >= 2 lanes per chain: the key tree costs six threefry blocks per transition
+// (two per split) that every lane of a chain would repeat.  Lanes g and g ^ 1 of the chain hash ONE block of each
+// split and exchange the word by shuffle: three blocks per lane instead of six, same keys bit for bit.
+__device__ __forceinline__ U2 split_index_shared(U2 key, uint32_t num, uint32_t i, int g) {
+  const uint32_t j = 2u * i + (uint32_t)(g & 1);  // element of random_bits(key, 2 num) this lane produces
+  const bool y = j >= num;
+  const U2 o = threefry2x32(key.x, key.y, y ? j - num : j, y ? j : j + num);
+  const uint32_t mine = y ? o.y : o.x;
+  const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+  return (g & 1) ? U2{other, mine} : U2{mine, other};
+}
+__device__ __forceinline__ U2 transition_key_shared(const TransArgs& a, long long chain, long long t, int g) {
+  if (a.ks.keys != nullptr) return U2{a.ks.keys[2 * chain], a.ks.keys[2 * chain + 1]};
+  const U2 kt = split_index_shared(U2{a.ks.root_key[0], a.ks.root_key[1]}, (uint32_t)a.ks.total_transitions, (uint32_t)t, g);
+  return split_index_shared(kt, (uint32_t)a.ks.total_chains, (uint32_t)(a.ks.chain_offset + chain), g);
+}
+// (k_a, k_b) = split(key, 2): bits = hash of counts (0, 2) and (1, 3); lane parity p hashes block (p, p + 2)
+__device__ __forceinline__ void split2_shared(U2 key, int g, U2& ka, U2& kb) {
+  const uint32_t p = (uint32_t)(g & 1);
+  const U2 o = threefry2x32(key.x, key.y, p, p + 2u);  // o.x = bits[p], o.y = bits[p + 2]
+  const uint32_t ox = __shfl_xor_sync(0xffffffffu, o.x, 1), oy = __shfl_xor_sync(0xffffffffu, o.y, 1);
+  ka = p ? U2{ox, o.x} : U2{o.x, ox};
+  kb = p ? U2{oy, o.y} : U2{o.y, oy};
+}
+
 // z = jax.random.normal(key, (D,)) distributed over the lane group (util.py:81-82).
 // Legacy threefry hashes the counters pairwise (i, i + D/2): when the layout is exact, D is
 // even and both halves of a pair live in the same lane, one block yields two normals.
