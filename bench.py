@@ -471,6 +471,15 @@ def bench_funnel(cx, args, cfg, wl_key, *, half_step=None, step_size=None, C=Non
             nominal_peak=nominal, frac_of_nominal=ach / nominal,
             nominal_source=f"148 SMs x 128 lanes x 2 x {clk or 1965.0:.0f} MHz (median SM clock of this run)",
             kernel_ms_median=med, **frec)
+        # issue-slot view: the bit-exact threefry stream is mandatory integer work the flop count leaves out
+        # (75 integer ops per block; per chain-transition 6 key-tree blocks + 1 accept uniform + D / 2 normal blocks)
+        int_ops = 75.0 * (7 + (D + 1) // 2)
+        slots = (unit * L / 2.0 + int_ops) * C * TPS / (med * 1e-3)
+        slot_peak = 148 * 128 * (clk or 1965.0) * 1e6
+        rec["roofline"]["issue_slots"] = {"mandatory_thread_instructions_per_chain_transition": unit * L / 2.0 + int_ops,
+                                          "of_which_integer_prng": int_ops, "achieved_per_s": slots, "peak_per_s": slot_peak,
+                                          "frac": slots / slot_peak,
+                                          "note": "FMA-equivalent slots (flops / 2) + threefry integer ops against 148 SMs x 128 lanes x clock"}
     if ess_samples > 0:
         rec.update(ess_record(cx, alg, C, D, ess_samples, burnin, init_fill, thin))
     return rec

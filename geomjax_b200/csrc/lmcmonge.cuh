@@ -144,7 +144,8 @@ __device__ __forceinline__ void monge_draw(const LAY& lay, R a2, MongeVecs<R, LA
 // Register cap for the small float layouts (EPL <= 10: c2's (10, 2)): 5 blocks of 128 threads per SM = 96 registers
 // (127 uncapped, no spills at 96): 20 instead of 16 resident warps per SM for c2's 27.7 warps per SM.  Measured: no
 // change (65.6 vs 65.9 ms per 2048-transition launch) -- the kernel is issue-bound, not occupancy-bound; the same cap
-// on lmc's (25, 4) layout changed nothing either (c3: 5.84e9 vs 5.88e9) and was not kept.
+// on lmc's (25, 4) layout changed nothing either (c3: 5.84e9 vs 5.88e9) and was not kept; 72 registers (every warp of c2
+// resident in one wave, 76 bytes of spill) was slower: 66.3 vs 62.5 ms.
 template <typename R, class Target, int EPL, int LPC, bool EXACT, bool UNIT, int HS = -1, bool LEAN = false>
 __global__ void __launch_bounds__(128, (sizeof(R) == 4 && EPL <= 10) ? 5 : 1) lmcmonge_kernel(const TransArgs a, const Target tg) {
   using LAY = Lay<EPL, LPC, EXACT>;
