@@ -495,7 +495,7 @@ def logreg_flops_per_eval(cfg):
     return gemm + 3 * 2.0 * Nr * D + D ** 3, gemm
 
 
-def bench_logreg(cx, args, cfg, *, C, T, K, W, label, ess_samples=0, burnin=0):
+def bench_logreg(cx, args, cfg, *, C, T, K, W, label, ess_samples=0, burnin=0, adapt_transitions=0):
     """rmhmc on logistic regression through geomjax_b200.rmhmc (lock-step rolling batch on the tcgen05 GEMMs):
     device-resident value, e2e, fixed-point histogram, tensor-pipe roofline."""
     g, torch, N = cx.g, cx.torch, cx.N
@@ -536,6 +536,7 @@ def bench_logreg(cx, args, cfg, *, C, T, K, W, label, ess_samples=0, burnin=0):
         rec["chain_evaluations_per_s"] = evals / (last_ms * 1e-3)
         rec["evaluations_per_chain_step"] = evals / (C * L * T)
         rec["rounds_last_launch"] = rounds
+        rec["kernels_in_graph_last_launch"] = 9 * rounds  # gpu_launches counts the graph launch once; a round is 9 kernels
         rec["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                            "traffic": None, "flops_per_chain_evaluation": f_eval, "gemm_flops_per_chain_evaluation": f_gemm,
                            "peak_source": f"tensor_3xtf32 = bf16_tflops_sustained ({src}) / 2 (tf32) / 3 (three MMAs per "
@@ -543,6 +544,23 @@ def bench_logreg(cx, args, cfg, *, C, T, K, W, label, ess_samples=0, burnin=0):
                                           "of the launch / launch time, ALL kernels of the round included"}
     if ess_samples > 0:
         rec.update(ess_record(cx, alg, C, D, ess_samples, burnin, torch.zeros))
+    if adapt_transitions > 0:
+        # c5's warm-up: per-chain dual averaging fused into the transition's epilogue (step_size_adaptation), timed here
+        # for `adapt_transitions` transitions from the initial position (adaptation/step_size_adaptation.py:143-201)
+        cx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res, ainfo = g.step_size_adaptation(g.rmhmc, target, initial_step_size=eps, metric_fn=target,
+                                            num_integration_steps=L).run(g.random.chain_keys(cx.root, 0, 1, C, chain_offset=cx.rank * C, total_chains=total_chains),
+                                                                         torch.zeros((C, D), device=cx.dev), adapt_transitions)
+        e1.record()
+        torch.cuda.synchronize()
+        ss = res.parameters["step_size"]
+        rec["step_size_adaptation"] = {"transitions": adapt_transitions,
+                                       "ms_per_transition": cx.max_over_ranks(e0.elapsed_time(e1)) / adapt_transitions,
+                                       "mean_acceptance": float(ainfo["acceptance_rate"].mean()),
+                                       "step_size_after": [float(ss.min()), float(ss.median()), float(ss.max())],
+                                       "note": "per-chain dual averaging in the kernel epilogue; initial step size = the config's"}
     return rec
 
 
@@ -669,7 +687,8 @@ def run_ours(args, cfg):
                                             label=CONFIGS["c4"]["name"], ess_samples=min(args.ess_samples, 640), burnin=40)
             elif s == "c5_shard":
                 c5 = CONFIGS["c5_shard"]
-                workloads[s] = bench_logreg(cx, args, c5, C=c5["chains_per_gpu"], T=2, K=2, W=1, label=c5["name"])
+                workloads[s] = bench_logreg(cx, args, c5, C=c5["chains_per_gpu"], T=2, K=2, W=1, label=c5["name"],
+                                            adapt_transitions=2)
         except Exception as e:  # a sub-record must never take the headline line down
             workloads[s] = {"error": f"{type(e).__name__}: {e}"[:300]}
     coll = None
