@@ -57,10 +57,19 @@ def _cpu_sampler(cfg, threads=0, half_step=None, step_size=None):
                           inverse_mass_matrix=np.ones(D, np.float32), threads=threads)
 
 
+def host_threads():
+    """Every host core this process may run on (torchrun exports OMP_NUM_THREADS=1: the OpenMP default is not it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_throughput(cfg, chains, transitions, threads=0, first=0, **kw):
-    """chain-leapfrog-steps/s of the C++ restatement on `threads` OpenMP threads; (value, seconds, threads, accept)."""
+    """chain-leapfrog-steps/s of the C++ restatement on `threads` OpenMP threads (0 = all host cores);
+    (value, seconds, threads, accept)."""
     from oracle import prng as P
-    smp = _cpu_sampler(cfg, threads, **kw)
+    smp = _cpu_sampler(cfg, threads or host_threads(), **kw)
     q0 = (np.ones if cfg["init_position"] == "ones" else np.zeros)((chains, cfg["D"]), np.float32)
     st = smp.init(q0)
     t0 = time.perf_counter()
@@ -105,8 +114,7 @@ def _cpu_sample_size(cfg, cores):
 def run_reference(args, cfg):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle import cpu
-    cores = cpu.lib().ocpu_max_threads()
+    cores = host_threads()
     L = cfg["num_integration_steps"]
     if _cpu_sampler(cfg) is None:  # funnel rmhmc: NumPy port only
         chains, tr = cfg["chains_per_gpu"], 50
@@ -720,8 +728,7 @@ def run_ours(args, cfg):
 
 def cpu_baseline_record(cfg):
     """The C++/OpenMP restatement on the box's host cores, bounded sample (~10-20 s); NumPy figure as a second field."""
-    from oracle import cpu
-    cores = cpu.lib().ocpu_max_threads()
+    cores = host_threads()
     L = cfg["num_integration_steps"]
     if _cpu_sampler(cfg) is None:
         v, w = numpy_throughput(cfg, cfg["chains_per_gpu"], 200)
