@@ -683,6 +683,9 @@ def run_ours(args, cfg):
                                         "accepts at eps ~ 1e-3 and therefore cannot mix in 1000 transitions.  The nearly "
                                         "Euclidean Monge metric (alpha2 = 1e-3) decorrelates the funnel's v over ~2,600 "
                                         "transitions, so this record thins by 64 to pass the R-hat gate")
+            elif s in ("c1", "c1_softabs"):
+                # the reference's own CPU-runnable case: examples/funnel as shipped / BASELINE configs[0], 1000 samples
+                workloads[s] = bench_funnel(cx, args, CONFIGS[s], s, TPS=1000, K=3, W=3, with_e2e=False, ess_samples=1000, burnin=0)
             elif s == "c3_shard":
                 c3 = CONFIGS["c3"]
                 rec = bench_funnel(cx, args, c3, "c3", TPS=64, K=5, W=3, with_e2e=False)
@@ -761,14 +764,14 @@ def main():
     ap.add_argument("--step-size", type=float, default=0.0)
     ap.add_argument("--ess-samples", type=int, default=1000)
     ap.add_argument("--ess-burnin", type=int, default=200)
-    ap.add_argument("--sub", default="default", help="comma list of sub-records (c2_omega_fixed,c3_shard,c4,c5_shard) or none")
+    ap.add_argument("--sub", default="default", help="comma list of sub-records (c1,c1_softabs,c2_omega_fixed,c3_shard,c4,c5_shard) or none")
     ap.add_argument("--no-collectives", dest="collectives", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.sub == "default":
-        args.sub = "c2_omega_fixed,c3_shard,c4,c5_shard" if args.workload == "c2" else "none"
+        args.sub = "c1,c1_softabs,c2_omega_fixed,c3_shard,c4,c5_shard" if args.workload == "c2" else "none"
     cfg = CONFIGS[args.workload]
     if args.impl == "reference":
         run_reference(args, cfg)
