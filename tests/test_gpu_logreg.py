@@ -248,3 +248,35 @@ def test_lockstep_midpoint_map_vs_oracle(cuda, Nrows, D, C):
     pn64 = pi.astype(np.float64) - he * (dT64 - g64)
     assert (np.abs(n("q") - qn64) / np.abs(qn64).max(axis=1, keepdims=True)).max() < 2e-4
     assert (np.abs(n("p") - pn64) / np.abs(pn64).max(axis=1, keepdims=True)).max() < 2e-4
+
+
+def test_lockstep_divergent_chains_are_data_not_errors(cuda):
+    """A step size far too large: the fixed point diverges / overflows for most chains.  As under jax.vmap, that is
+    data -- the launch terminates (round bound), diverged proposals are rejected (NaN energy -> delta = -inf), the
+    returned state stays finite and equals the input for rejected chains, and the oracle rejects the same chains."""
+    import torch
+    import geomjax_b200 as g
+    X, y = T.make_logreg_data(200, 8, seed=1)
+    tgt = T.LogisticRegression(X, y, 0.01)
+    rng = np.random.default_rng(3)
+    C = 64
+    q = (0.1 * rng.standard_normal((C, 8))).astype(np.float32)
+    keys = rng.integers(0, 2 ** 32, size=(C, 2), dtype=np.uint64).astype(np.uint32)
+    target = g.logistic_regression(_t(X, cuda), _t(y, cuda), 0.01)
+    alg = g.rmhmc(target, 20.0, target, 2)
+    st = alg.init(_t(q, cuda))
+    new, info = alg.step(_t(keys, cuda), st)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(new.position).all()) and bool(torch.isfinite(new.logdensity).all())
+    rej = ~info.is_accepted
+    assert bool((new.position[rej] == st.position[rej]).all())
+    with np.errstate(all="ignore"):
+        _, oinfo = S.rmhmc_step(keys, S.rmhmc_init(q, tgt), tgt, 20.0, 2)
+    # the bulk of the chains is rejected on both sides; individual borderline chains may differ
+    assert float(rej.float().mean()) > 0.5 and (~oinfo.is_accepted).mean() > 0.5
+    agree = (info.is_accepted.cpu().numpy() == oinfo.is_accepted).mean()
+    assert agree > 0.8, agree
+    # and a fused multi-transition launch with such chains still terminates and keeps the state finite
+    fst, samples, _ = g.run_fused(alg.step, g.random.PRNGKey(1), st, 3, return_samples=True)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(fst.position).all()) and bool(torch.isfinite(samples).all())
