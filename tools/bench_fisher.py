@@ -7,7 +7,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import geomjax_b200 as g
-from oracle.targets import make_logreg_data
+from bench.data import make_logreg_data
 
 
 def timed(fn, reps=10):
@@ -36,9 +36,10 @@ for (N, D, C) in ((1000, 25, 16384), (10000, 100, 2048)):
     ms, h = timed(lambda: t.quadratic_forms(A))
     print(f"quadratic_forms  N={N} D={D} C={C}: {ms:.3f} ms per call; algorithmic {2.0 * N * P * C / ms / 1e9:.2f} TFLOP/s "
           f"(x3 TF32 passes = {6.0 * N * P * C / ms / 1e9:.2f} tensor TFLOP/s)")
-    # one lock-step evaluation of the implicit-midpoint map for all chains (both GEMMs + batched Cholesky + O(ND) kernels)
+    # one lock-step round for explicit inputs (both GEMMs + batched Cholesky / inverse + O(ND) kernels)
     p = torch.randn((C, D), device=dev) * (N ** 0.5) * 0.3
-    ms, out = timed(lambda: t.midpoint_map(q, p, q, p, 0.05), reps=5)
-    feval = 2.0 * N * D * D + 10.0 * N * D + D ** 3
-    print(f"midpoint_map     N={N} D={D} C={C}: {ms:.3f} ms per call = {C / ms * 1e3:.0f} chain-evaluations/s; "
+    plan = g.LockstepPlan(t, C, dev)
+    ms, out = timed(lambda: plan.evaluate(0, q, p, half_step=0.05), reps=5)
+    feval = 2.0 * N * D * (D + 1) + 6.0 * N * D + D ** 3
+    print(f"lockstep round   N={N} D={D} C={C}: {ms:.3f} ms per call = {C / ms * 1e3:.0f} chain-evaluations/s; "
           f"algorithmic {feval * C / ms / 1e9:.2f} TFLOP/s")
