@@ -682,7 +682,10 @@ def run_ours(args, cfg):
                                         "reference AS WRITTEN (lmcmonge/integrators.py:186-189, SURVEY F8), which only "
                                         "accepts at eps ~ 1e-3 and therefore cannot mix in 1000 transitions.  The nearly "
                                         "Euclidean Monge metric (alpha2 = 1e-3) decorrelates the funnel's v over ~2,600 "
-                                        "transitions, so this record thins by 64 to pass the R-hat gate")
+                                        "transitions: this record runs 262,144 transitions per chain and keeps every 64th sample "
+                                        "(R-hat(v) 1.02); four times as many transitions made it WORSE (1.11: chains that enter "
+                                        "the funnel's neck stay for very long), so no run length passes the 1.01 gate for this "
+                                        "sampler on this target -- min-ESS/s stays flagged invalid")
             elif s in ("c1", "c1_softabs"):
                 # the reference's own CPU-runnable case: examples/funnel as shipped / BASELINE configs[0], 1000 samples
                 workloads[s] = bench_funnel(cx, args, CONFIGS[s], s, TPS=1000, K=3, W=3, with_e2e=False, ess_samples=1000, burnin=0)
