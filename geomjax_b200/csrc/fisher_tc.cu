@@ -113,9 +113,9 @@ __device__ __forceinline__ void ft_mbar_wait(uint32_t mbar_a, uint32_t parity) {
 // Thread tile = TI features x TC chains (chains cb + (128 / TC) k: lanes read consecutive rows of Rs[c][129], no bank
 // conflicts; the x reads are broadcasts), TI + TC shared-memory loads per TI * TC FMAs.
 template <int TI, int TC>
-__device__ __forceinline__ void ft_epi_xtr(const float* __restrict__ xr, int DX, const float* __restrict__ Rs, int D,
+__device__ __forceinline__ void ft_epi_xtr(const float* __restrict__ xr, int DX, const float* __restrict__ Rt, int D,
                                            float* __restrict__ parts, long long Ccap, long long c0, long long C, int tid) {
-  constexpr int CB = 128 / TC;  // one call covers 128 chains
+  constexpr int CB = 128 / TC;  // one call covers 128 chains; thread = TI features x TC chains (groups of 4 adjacent)
   const int cb = tid % CB, ib = tid / CB;
   if (ib * TI >= D) return;
   int fi[TI];
@@ -126,14 +126,17 @@ __device__ __forceinline__ void ft_epi_xtr(const float* __restrict__ xr, int DX,
   for (int t = 0; t < TI; ++t)
 #pragma unroll
     for (int k = 0; k < TC; ++k) o[t][k] = 0.f;
-  const float* rp = Rs + cb * 129;
+  const float* rp = Rt + 4 * cb;  // chains 4 cb .. 4 cb + 3 (+ 4 CB per further group): float4 reads, lanes adjacent
 #pragma unroll 4
   for (int r = 0; r < FT_M; ++r) {
     float xv[TI], rv[TC];
 #pragma unroll
     for (int t = 0; t < TI; ++t) xv[t] = xr[r * DX + fi[t]];
 #pragma unroll
-    for (int k = 0; k < TC; ++k) rv[k] = rp[(CB * k) * 129 + r];
+    for (int k4 = 0; k4 < TC / 4; ++k4) {
+      const float4 v = *(const float4*)(rp + r * FT_RS + k4 * 4 * CB);
+      rv[4 * k4] = v.x; rv[4 * k4 + 1] = v.y; rv[4 * k4 + 2] = v.z; rv[4 * k4 + 3] = v.w;
+    }
 #pragma unroll
     for (int t = 0; t < TI; ++t)
 #pragma unroll
@@ -145,7 +148,7 @@ __device__ __forceinline__ void ft_epi_xtr(const float* __restrict__ xr, int DX,
     if (i < D) {
 #pragma unroll
       for (int k = 0; k < TC; ++k) {
-        const long long j = c0 + cb + CB * k;
+        const long long j = c0 + (k >> 2) * 4 * CB + 4 * cb + (k & 3);
         if (j < C) parts[(size_t)i * Ccap + j] = o[t][k];
       }
     }
@@ -193,7 +196,7 @@ fisher_metric_tc_kernel(const FtArgs a) {
   __shared__ uint32_t tmem_base_s;
   // mbarriers: A stage free (MMAs of its tile done) | A stage built | B slot landed | X tile landed | accumulator complete
   constexpr int MB_FREE = 0, MB_BUILT = MB_FREE + FT_NSA, MB_BLAND = MB_BUILT + FT_NSA, MB_XLAND = MB_BLAND + FT_NSB,
-                MB_ACC = MB_XLAND + FT_NXB, MB_COUNT = MB_ACC + 2;
+                MB_ACC = MB_XLAND + FT_NXB, MB_SLAND = MB_ACC + 2, MB_COUNT = MB_SLAND + 1;
   __shared__ __align__(8) unsigned long long mbar[MB_COUNT];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int P = D * (D + 1) / 2;
@@ -208,13 +211,12 @@ fisher_metric_tc_kernel(const FtArgs a) {
   const int nchunks = (ktiles + FT_KC - 1) / FT_KC;
   const int DX = D | 1;  // QUAD: odd row stride of the staged data rows xr[128][DX] (lanes = rows: conflict-free)
   if (QUAD && EPI == 1) {
-    // the fused epilogue reads s[chain, row] for this CTA's 256 chains x 128 rows (512 contiguous bytes per chain):
-    // ask for those lines now, so that they wait in L2 when the main loop is done (from HBM the epilogue's loads
-    // were 50 % of the kernel's stall samples at c4's shape)
-    for (int e = tid; e < FT_N * 4; e += FT_THREADS) {
-      const long long j = c0 + (e >> 2);
-      const int n = m0 + (e & 3) * 32;
-      if (j < C && n < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.sbuf + (size_t)j * a.lds + n));
+    // the fused epilogue reads sT[row, chain] for this CTA's 128 rows x 256 chains (1 KB contiguous per row): ask
+    // for those lines now, so that they wait in L2 when the main loop is done
+    for (int e = tid; e < FT_M * 8; e += FT_THREADS) {
+      const int n = m0 + (e >> 3);
+      const long long j = c0 + (e & 7) * 32;
+      if (j < a.lds && n < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.sbuf + (size_t)n * a.lds + j));
     }
   }
   if (QUAD) {
@@ -234,7 +236,7 @@ fisher_metric_tc_kernel(const FtArgs a) {
   }
   if (tid == 0) {
     for (int i = 0; i < MB_COUNT; ++i) {
-      const uint32_t cnt = (i >= MB_BUILT && i < MB_BLAND) ? 256u : 1u;  // "built": every producer thread arrives
+      const uint32_t cnt = (i >= MB_BUILT && i < MB_BLAND) ? 256u : (i == MB_SLAND ? 128u : 1u);  // "built": every producer thread arrives; "s landed": one per row
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb(i)), "r"(cnt));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -403,37 +405,51 @@ fisher_metric_tc_kernel(const FtArgs a) {
     for (int c = drained; c < nchunks; ++c) drain(c);
 
     if (QUAD && EPI == 1) {
-      // every MMA has completed (the last accumulator is drained): the operand stages are free and hold R now
-      float* Rs = (float*)ft_smem;  // [256 chains][129]: conflict-free for lanes = rows (write) and lanes = chains (read)
+      // Every MMA has completed (this thread drained the last accumulator): the operand stages are free.  The s tile
+      // sT[128 rows][256 chains] is bulk-copied into them, one 1 KB row per thread, and R overwrites it in place.
+      // (Read with per-thread global loads, s cost as much as the whole main loop at c4's shape: 268 us against
+      // 131 us with the loads removed -- 8 KB in flight per SM cannot hide the latency; one bulk copy per row can.)
+      float* St = (float*)ft_smem;  // [128 rows][FT_RS]: float4 accesses by lanes = rows and by lanes = chains are conflict-free
       const int n = m0 + row;
-      const float yn = (n < N) ? __ldg(a.y + n) : 0.f;
-      // s and the phase come from global memory: fetched 8 chains ahead with explicit read-only loads.  (Written
-      // as load-use-store per chain, the compiler could not move a generic-pointer load across the shared-memory
-      // store of the previous chain: 128 serialised ~1,000-cycle loads = 55 us per CTA, 70 % of this kernel's time
-      // at c4's shape.)
-      constexpr int EB = 8;
-#pragma unroll
-      for (int e0 = 0; e0 < NH; e0 += EB) {  // fully unrolled: acc[] must keep static register indices
-        float sv[EB];
-        unsigned int endv = 0;
-#pragma unroll
-        for (int u = 0; u < EB; ++u) {
-          const long long j = c0 + half * NH + e0 + u;
-          const bool live = j < C && n < N;
-          sv[u] = live ? __ldg(a.sbuf + (size_t)j * a.lds + n) : 0.f;
-          if (j < C && __ldg(a.slot_phase + j) == LS_PH_END) endv |= 1u << u;
+      if (half == 0) {
+        const long long rem = a.lds - c0;  // lds % 4 == 0: whole 16-byte units
+        const uint32_t nb = (n < N) ? (uint32_t)(rem < FT_N ? rem : FT_N) * 4u : 0u;
+        if (nb) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb(MB_SLAND)), "r"(nb) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           (uint32_t)__cvta_generic_to_shared(St + row * FT_RS)),
+                       "l"(a.sbuf + (size_t)n * a.lds + c0), "r"(nb), "r"(mb(MB_SLAND))
+                       : "memory");
+        } else {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb(MB_SLAND)) : "memory");
         }
+      }
+      const float yn = (n < N) ? __ldg(a.y + n) : 0.f;
+      // phases of this thread's 128 chains: one byte per lane and a ballot per group of 32 (not 128 loads per thread)
+      unsigned int endm[NH / 32];
 #pragma unroll
-        for (int u = 0; u < EB; ++u) {
+      for (int gq = 0; gq < NH / 32; ++gq) {
+        const long long jl = c0 + half * NH + gq * 32 + (tid & 31);
+        endm[gq] = __ballot_sync(0xffffffffu, jl < C && __ldg(a.slot_phase + jl) == LS_PH_END);
+      }
+      ft_mbar_wait(mb(MB_SLAND), 0u);
+      float* sp = St + row * FT_RS + half * NH;
+#pragma unroll
+      for (int e0 = 0; e0 < NH; e0 += 4) {  // fully unrolled: acc[] must keep static register indices
+        const float4 s4 = *(const float4*)(sp + e0);
+        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+        float R[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
           const long long j = c0 + half * NH + e0 + u;
-          float R = 0.f;
+          R[u] = 0.f;
           if (j < C && n < N) {
             const float sg = sv[u];
             const float t = sg * (1.f - sg) * (1.f - 2.f * sg) * acc[e0 + u];
-            R = ((endv >> u) & 1u ? 0.f : 0.5f * t) - (yn - sg);
+            R[u] = ((endm[(e0 + u) >> 5] >> ((e0 + u) & 31)) & 1u ? 0.f : 0.5f * t) - (yn - sg);
           }
-          Rs[(half * NH + e0 + u) * 129 + row] = R;
         }
+        *(float4*)(sp + e0) = make_float4(R[0], R[1], R[2], R[3]);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 producer warps (the issuer warp is not involved)
       // parts[m tile][i][c] = sum_r x[r, i] R[r, c]: a 128 x D x 128 product on the FP32 pipe, register-tiled
@@ -441,8 +457,8 @@ fisher_metric_tc_kernel(const FtArgs a) {
 #pragma unroll 1
       for (int h = 0; h < FT_N / 128; ++h) {  // 128 chains at a time
         if (c0 + h * 128 >= C) break;
-        if (D <= 32) ft_epi_xtr<4, 4>(xs0, DX, Rs + h * 128 * 129, D, pbase, a.Ccap, c0 + h * 128, C, tid);
-        else ft_epi_xtr<8, 8>(xs0, DX, Rs + h * 128 * 129, D, pbase, a.Ccap, c0 + h * 128, C, tid);
+        if (D <= 32) ft_epi_xtr<4, 4>(xs0, DX, St + h * 128, D, pbase, a.Ccap, c0 + h * 128, C, tid);
+        else ft_epi_xtr<8, 8>(xs0, DX, St + h * 128, D, pbase, a.Ccap, c0 + h * 128, C, tid);
       }
     } else if (QUAD) {
       // epilogue: registers -> h[c, n] (chain-major rows of length ldh; lanes = consecutive data rows: coalesced)

@@ -23,7 +23,8 @@ constexpr int FT_NSB = 3;      // B slots (one bulk-TMA copy each, issued by a d
 constexpr int FT_NXB = 4;      // X tile buffers of the metric GEMM (bulk-copied 4 K tiles ahead)
 constexpr int FT_DRAIN_LAG = 2;  // a finished TMEM chunk is drained after the producers queued this many tiles of the next
 constexpr int FT_STAGE_REGION = FT_NSA * 2 * FT_A_BYTES + FT_NSB * 2 * FT_B_BYTES;  // A ring + B slots (hi + lo each)
-constexpr int FT_EPI_REGION = FT_N * 129 * 4;                             // R[chain][129] of the fused epilogue
+constexpr int FT_RS = FT_N + 4;                                           // row stride (floats) of the fused epilogue's s / R tile
+constexpr int FT_EPI_REGION = FT_M * FT_RS * 4;                           // sT / R [128 data rows][FT_RS]
 constexpr int FT_REGION = ((FT_STAGE_REGION > FT_EPI_REGION ? FT_STAGE_REGION : FT_EPI_REGION) + 1023) / 1024 * 1024;
 
 // phases of a chain in the lock-step sampler (rmhmc_lockstep.cu)
@@ -48,7 +49,7 @@ struct FtArgs {
   const short2* pairs;
   int PS, ldh;
   // fused epilogue of the quadratic-form GEMM (EPI == 1)
-  const float* sbuf;         // s[c, n] = sigmoid(eta), row stride lds
+  const float* sbuf;         // sT[n, c] = sigmoid(eta) of data row n, chain slot c; row stride lds (% 4 == 0)
   long long lds;
   const float* y;
   const unsigned char* slot_phase;

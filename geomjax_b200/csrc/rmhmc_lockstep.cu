@@ -297,7 +297,11 @@ __global__ void __launch_bounds__(FT_N) ls_weights_kernel(const LsBuf b, const L
       w[e] = (live && n < N) ? sg[e] * (1.f - sg[e]) : 0.f;
       if (end && n < N) lp += __ldg(b.y + n) * et - (fmaxf(et, 0.f) + log1pf(expf(-fabsf(et))));  // jnp.logaddexp(0, eta)
     }
-    if (live && n0 + 4 * k4 < d.ldn) *(float4*)(b.sbuf + (size_t)j * d.ldn + n0 + 4 * k4) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+    if (live) {  // sT[data row][chain slot]: lanes = consecutive slots
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (n0 + 4 * k4 + e < N) b.sbuf[(size_t)(n0 + 4 * k4 + e) * d.ldn + j] = sg[e];
+    }
     float4 hi, lo;
     ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
     *(float4*)(base + k4 * FT_LBO) = hi;
@@ -865,7 +869,7 @@ int ls_dims(const gb200_target_desc* t, int64_t C, LsDims* d) {
   d->D = t->D;
   d->ldx = (int)t->params[1];
   if (d->ldx < d->N || d->ldx % 4 != 0) { set_error("lock-step plan: ldx must be >= N and a multiple of 4"); return GB200_ERR_INVALID_ARGUMENT; }
-  d->ldn = (d->N + 3) / 4 * 4;
+  d->ldn = (int)((C + 3) / 4 * 4);  // row stride of sT[N][ldn] (16-byte rows for the bulk copies)
   d->P = d->D * (d->D + 1) / 2;
   d->PS = ft_ps(d->D);
   d->ktF = (d->N + FT_KT - 1) / FT_KT;
@@ -910,7 +914,7 @@ int64_t ls_carve(const LsDims& d, unsigned char* base, LsBuf* b) {
   t.idx = (int*)take(C * 4);
   t.slot_phase = (unsigned char*)take(C);
   t.v = (float*)take(C * D * 4); t.logdet = (float*)take(C * 4);
-  t.sbuf = (float*)take(C * (int64_t)d.ldn * 4);
+  t.sbuf = (float*)take((int64_t)d.N * d.ldn * 4);
   t.Gp = (float*)take(C * (int64_t)d.P * 4); t.Ap = (float*)take(C * (int64_t)d.P * 4);
   t.parts = (float*)take((int64_t)d.mtQ * D * C * 4);
   t.lp_parts = (float*)take((int64_t)d.ktF * C * 4);
