@@ -175,16 +175,28 @@ __device__ __forceinline__ void ft_epi_xtr(const float* __restrict__ xr, int DX,
 //   parts[m tile][i][c] = sum_{n in tile} x_ni R[n, c]   (summed over the m tiles by ls_reduce_kernel):
 //   X^T R = dT/dq - X^T(y - s), the data part of dH/dq of rmhmc's implicit-midpoint map, without h or R ever
 //   going to HBM.
+#ifdef GB_FT_TIMING
+__device__ unsigned long long ft_dbg[8192 * 16];
+__device__ __forceinline__ unsigned long long ft_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define FT_STAMP(k) ft_dbg[(((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) % 4096 + (QUAD ? 4096 : 0)) * 16 + (k)] = ft_now()
+#else
+#define FT_STAMP(k)
+#endif
 template <bool QUAD, int EPI>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 fisher_metric_tc_kernel(const FtArgs a) {
-  const float* __restrict__ Xtile = a.Xtile;
+  if (threadIdx.x == 0) { FT_STAMP(0); }
   const int N = a.N, D = a.D;
-  const unsigned char* __restrict__ Wt = a.Wt;
+  // split-K (metric GEMM, packed output): grid z = part of the K range; parts write partial sums side by side
+  const int ktiles_all = QUAD ? a.PS / FT_KT : (N + FT_KT - 1) / FT_KT;
+  const int kper = (!QUAD && a.ksplit > 1) ? (ktiles_all + a.ksplit - 1) / a.ksplit : ktiles_all;
+  const int kt0 = QUAD ? 0 : (int)blockIdx.z * kper;
+  const float* __restrict__ Xtile = a.Xtile + (size_t)kt0 * D * FT_XS;
+  const unsigned char* __restrict__ Wt = a.Wt + (size_t)kt0 * (2 * FT_B_BYTES);
   const long long C = a.n_active ? (long long)*a.n_active : a.C;  // lock-step sampler: chains still iterating
   if ((long long)blockIdx.y * FT_N >= C) return;
-  const float alpha = a.alpha;
-  float* __restrict__ G = a.out;
+  const float alpha = (QUAD || blockIdx.z == 0) ? a.alpha : 0.f;
+  float* __restrict__ G = a.out + (QUAD ? 0 : (size_t)blockIdx.z * a.split_stride);
   const float* __restrict__ Xt = a.Xt;
   const int ldx = a.ldx;
   const short2* __restrict__ pairs = a.pairs;
@@ -207,24 +219,23 @@ fisher_metric_tc_kernel(const FtArgs a) {
   auto mb = [&](int i) { return mb0 + 8u * (uint32_t)i; };
   const uint32_t xbytes = (uint32_t)D * FT_XS * 4;
   const uint32_t bbytes = 2 * FT_B_BYTES;
-  const int ktiles = QUAD ? PS / FT_KT : (N + FT_KT - 1) / FT_KT;
+  const int ktiles = min(kper, ktiles_all - kt0);  // >= 1 (ft_pick_ksplit)
   const int nchunks = (ktiles + FT_KC - 1) / FT_KC;
   const int DX = D | 1;  // QUAD: odd row stride of the staged data rows xr[128][DX] (lanes = rows: conflict-free)
-  if (QUAD && EPI == 1) {
-    // the fused epilogue reads sT[row, chain] for this CTA's 128 rows x 256 chains (1 KB contiguous per row): ask
-    // for those lines now, so that they wait in L2 when the main loop is done
-    for (int e = tid; e < FT_M * 8; e += FT_THREADS) {
-      const int n = m0 + (e >> 3);
-      const long long j = c0 + (e & 7) * 32;
-      if (j < a.lds && n < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.sbuf + (size_t)n * a.lds + j));
-    }
-  }
   if (QUAD) {
+    // the CTA's 128 data rows, staged once, 16 loads in flight per thread
     float* xr = xs0;
-    for (int e = tid; e < FT_M * D; e += FT_THREADS) {
-      const int i = e / FT_M, r = e - i * FT_M;
-      const int n = m0 + r;
-      xr[r * DX + i] = (n < N) ? Xt[(size_t)i * ldx + n] : 0.f;
+    const int r = tid & (FT_M - 1), n = m0 + r;
+    if (tid < 2 * FT_M) {
+      const float* xp = Xt + min(n, N - 1);  // unconditional loads (clamped indices) so that all 16 are issued back to back
+      for (int i0 = tid >> 7; i0 < D; i0 += 32) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldg(xp + (size_t)min(i0 + 2 * u, D - 1) * ldx);
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          if (i0 + 2 * u < D) xr[r * DX + i0 + 2 * u] = n < N ? v[u] : 0.f;
+      }
     }
   }
 
@@ -245,6 +256,7 @@ fisher_metric_tc_kernel(const FtArgs a) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
+  if (threadIdx.x == 0) { FT_STAMP(1); }
 
   auto bulk = [&](void* dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -260,7 +272,7 @@ fisher_metric_tc_kernel(const FtArgs a) {
       // B tile j -> slot j % FT_NSB as soon as the MMAs of tile j - FT_NSB (the slot's previous user) are done
       for (int j = 0; j < ktiles; ++j) {
         if (j >= FT_NSB) ft_mbar_wait(mb(MB_FREE + (j - FT_NSB) % FT_NSA), (uint32_t)(((j - FT_NSB) / FT_NSA) & 1));
-        bulk(Bslot + (size_t)(j % FT_NSB) * bbytes, Wt + ((size_t)ct * ktiles + j) * bbytes, bbytes, mb(MB_BLAND + j % FT_NSB));
+        bulk(Bslot + (size_t)(j % FT_NSB) * bbytes, Wt + ((size_t)ct * ktiles_all + j) * bbytes, bbytes, mb(MB_BLAND + j % FT_NSB));
       }
     }
     if (tid == 256) {
@@ -282,6 +294,8 @@ fisher_metric_tc_kernel(const FtArgs a) {
         const uint64_t b_hi = dB0 + (uint64_t)slot * 2 * BTILE16, b_lo = b_hi + BTILE16;
         const int chunk = j / FT_KC;
         const uint32_t td = tmem_d + (uint32_t)((chunk & 1) * FT_N);
+        if (j == 0) { FT_STAMP(2); }
+        if (j == ktiles - 1) { FT_STAMP(3); }
 #pragma unroll
         for (int k8 = 0; k8 < FT_KT / 8; ++k8) {
           const uint64_t adv = (uint64_t)k8 * ((2u * FT_LBO) >> 4);  // one MMA consumes 8 tf32 = 2 core matrices along K
@@ -299,6 +313,16 @@ fisher_metric_tc_kernel(const FtArgs a) {
   } else {
     // ------------------------------------------------------------------ producers / drainers
     const int row = tid & 127, half = tid >> 7;
+    if (QUAD && EPI == 1) {
+      // The fused epilogue reads sT[row, chain] for this CTA's 128 rows x 256 chains (1 KB contiguous per row): ask
+      // for those lines now, so that they wait in L2 when the main loop is done.  (Issued at kernel entry, these
+      // prefetches queued in front of the data-row loads of the prologue.)
+      for (int e = tid; e < FT_M * 8; e += 2 * FT_M) {
+        const int n = m0 + (e >> 3);
+        const long long j = c0 + (e & 7) * 32;
+        if (j < a.lds && n < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.sbuf + (size_t)n * a.lds + j));
+      }
+    }
     int pi = 0, pj = 0;  // pair (i, j), i <= j, of row m0 + row
     if (!QUAD) {
       int m = m0 + row;
@@ -402,7 +426,9 @@ fisher_metric_tc_kernel(const FtArgs a) {
         drained = kt / FT_KC;
       }
     }
+    if (tid == 0) { FT_STAMP(4); }
     for (int c = drained; c < nchunks; ++c) drain(c);
+    if (tid == 0) { FT_STAMP(5); }
 
     if (QUAD && EPI == 1) {
       // Every MMA has completed (this thread drained the last accumulator): the operand stages are free.  The s tile
@@ -432,7 +458,9 @@ fisher_metric_tc_kernel(const FtArgs a) {
         const long long jl = c0 + half * NH + gq * 32 + (tid & 31);
         endm[gq] = __ballot_sync(0xffffffffu, jl < C && __ldg(a.slot_phase + jl) == LS_PH_END);
       }
+      if (tid == 0) { FT_STAMP(8); }
       ft_mbar_wait(mb(MB_SLAND), 0u);
+      if (tid == 0) { FT_STAMP(9); }
       float* sp = St + row * FT_RS + half * NH;
 #pragma unroll
       for (int e0 = 0; e0 < NH; e0 += 4) {  // fully unrolled: acc[] must keep static register indices
@@ -452,6 +480,7 @@ fisher_metric_tc_kernel(const FtArgs a) {
         *(float4*)(sp + e0) = make_float4(R[0], R[1], R[2], R[3]);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 producer warps (the issuer warp is not involved)
+      if (tid == 0) { FT_STAMP(10); }
       // parts[m tile][i][c] = sum_r x[r, i] R[r, c]: a 128 x D x 128 product on the FP32 pipe, register-tiled
       float* pbase = a.parts + (size_t)blockIdx.x * D * a.Ccap;
 #pragma unroll 1
@@ -470,27 +499,43 @@ fisher_metric_tc_kernel(const FtArgs a) {
           if (c < C) G[(size_t)c * ldh + n] = acc[e];
         }
       }
+    } else if (a.packed) {
+      // epilogue, packed pairs G[c, m] (row stride a.packed, a multiple of 4 floats): the 128 x 256 tile goes through
+      // the freed operand stages (every MMA has completed) and leaves as one bulk store of 512 bytes per chain.
+      // (As 128 4-byte stores per thread this took 9-29 us per CTA at c4's shape, a third of the CTA's life.)
+      float* Ss = (float*)ft_smem;  // [256 chains][128 pairs]
+      const float dg = (pi >= 0 && pi == pj) ? alpha : 0.f;  // rows beyond P hold zeros (their A rows were zero)
+#pragma unroll
+      for (int e = 0; e < NH; ++e) Ss[(half * NH + e) * FT_M + row] = acc[e] + dg;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const long long c = c0 + tid;
+      const int nrow = min(FT_M, a.packed - m0);
+      if (c < C && nrow > 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(G + (size_t)c * a.packed + m0),
+                     "r"((uint32_t)__cvta_generic_to_shared(Ss + tid * FT_M)), "r"((uint32_t)nrow * 4u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
     } else if (pi >= 0) {
-      // epilogue: registers -> G[c, i, j] (+ alpha on the diagonal), or packed pairs G[c, m] (lanes = consecutive
-      // pairs of one chain: coalesced)
+      // epilogue: registers -> G[c, i, j] (+ alpha on the diagonal)
 #pragma unroll
       for (int e = 0; e < NH; ++e) {
         const long long c = c0 + half * NH + e;
         if (c < C) {
           const float v = acc[e] + (pi == pj ? alpha : 0.f);
-          if (a.packed) {
-            G[(size_t)c * P + m0 + row] = v;
-          } else {
-            float* g = G + (size_t)c * D * D;
-            g[pi * D + pj] = v;
-            g[pj * D + pi] = v;
-          }
+          float* g = G + (size_t)c * D * D;
+          g[pi * D + pj] = v;
+          g[pj * D + pi] = v;
         }
       }
     }
   }
+  if (tid == 0) { FT_STAMP(6); }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (tid == 0) { FT_STAMP(7); }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(2 * FT_N));
   }
@@ -577,7 +622,9 @@ int ft_launch_pairs(short2* pairs, int D, cudaStream_t s) {
 }
 int ft_launch_metric_gemm(const FtArgs& a, long long ctiles, cudaStream_t s) {
   const int P = a.D * (a.D + 1) / 2;
-  dim3 grid((unsigned)((P + FT_M - 1) / FT_M), (unsigned)ctiles);
+  const int S = a.ksplit > 1 ? a.ksplit : 1;
+  if (S > 1 && !a.packed) { set_error("metric GEMM: split-K needs the packed output"); return GB200_ERR_INVALID_ARGUMENT; }
+  dim3 grid((unsigned)((P + FT_M - 1) / FT_M), (unsigned)ctiles, (unsigned)S);
   fisher_metric_tc_kernel<false, 0><<<grid, FT_THREADS, ft_metric_smem(a.D), s>>>(a);
   GB_CHECK_LAUNCH();
   return GB200_OK;
@@ -694,3 +741,9 @@ extern "C" int64_t gb200_logreg_fisher_metric_workspace(const gb200_target_desc*
   // pre-split W^T tiles (hi + lo), see fisher_weights_kernel, + the re-tiled X (fisher_xtile_kernel)
   return ctiles * ktiles * 2 * FT_B_BYTES + ktiles * (int64_t)t->D * FT_XS * 4;
 }
+
+#ifdef GB_FT_TIMING
+extern "C" int gb200_debug_ft_stamps(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, gb::ft_dbg, sizeof(unsigned long long) * 8192 * 16);
+}
+#endif

@@ -43,7 +43,9 @@ struct FtArgs {
   const int* n_active;       // device: number of live columns (lock-step sampler); CTAs beyond it exit at once
   float alpha;
   float* out;                // metric: G [C, D, D] (packed == 0) or packed pairs [C, P]; quadratic forms: h [C, ldh]
-  int packed;
+  int packed;                // 0: dense G [C, D, D]; > 0: packed pairs, value = row stride in floats (>= P)
+  int ksplit;                // metric GEMM, packed output only: the K range (data rows) is cut into ksplit parts (grid z);
+  long long split_stride;    // part z writes its partial sums to out + z * split_stride; the consumer adds them (0/1 = off)
   const float* Xt;           // quadratic forms: X^T [D, ldx]
   int ldx;
   const short2* pairs;
@@ -66,6 +68,22 @@ int ft_launch_quad_gemm(const FtArgs& a, long long ctiles, int epi, cudaStream_t
 int ft_launch_quad_b_packed(const float* Ap, int D, long long C, const int* n_active, unsigned char* Bt, long long ctiles,
                             cudaStream_t s);
 int ft_set_attributes(int D);  // cudaFuncSetAttribute for both GEMM kernels (outside stream capture)
+// Split of the metric GEMM's K range that minimises waves x (K tiles per CTA + fixed cost) on `sms` SMs (one CTA per
+// SM).  c4's shape: 3 pair tiles x 64 chain tiles = 192 CTAs = 1.3 waves of 148, i.e. two full-length waves; cut in
+// two it is three waves of half the length.  Only taken when the model gains > 5 % (each part costs a pass
+// over the packed output).
+inline int ft_pick_ksplit(long long ctas, int ktiles, int sms) {
+  int best = 1;
+  double t1 = 0, tb = 0;
+  for (int S = 1; S <= 4; ++S) {
+    const int kper = (ktiles + S - 1) / S;
+    if (kper < 8 || (long long)(S - 1) * kper >= ktiles) break;  // every part keeps at least one K tile
+    const double t = (double)((ctas * S + sms - 1) / sms) * (kper + 12);  // fixed cost of a CTA (prologue, last drain, epilogue) ~ 12 K tiles
+    if (S == 1) t1 = tb = t;
+    else if (t < 0.95 * t1 && t < tb) { tb = t; best = S; }
+  }
+  return best;
+}
 inline int ft_ps(int D) { const int P = D * (D + 1) / 2; return (P + FT_KT - 1) / FT_KT * FT_KT; }
 inline size_t ft_metric_smem(int D) { return (size_t)FT_REGION + FT_NXB * (size_t)D * FT_XS * 4 + 1024; }
 inline size_t ft_quad_smem(int D) { return (size_t)FT_REGION + (size_t)FT_M * (D | 1) * 4 + 1024; }

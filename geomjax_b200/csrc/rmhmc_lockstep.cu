@@ -31,7 +31,7 @@
 namespace gb {
 
 struct LsDims {
-  int N, D, ldx, ldn, P, PS, ktF, ktQ, mtQ, BS, NB, nblk, fthreads, fwarp, fsmem_floats;
+  int N, D, ldx, ldn, P, PS, ktF, ktQ, mtQ, BS, NB, nblk, fthreads, fwarp, fsmem_floats, ksplit;
   long long Ccap, ctiles;
   float alpha;
 };
@@ -137,25 +137,25 @@ __global__ void __launch_bounds__(1024) ls_compact_kernel(const LsBuf b, const L
   __shared__ int wsum[32];
   __shared__ int total_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // each thread owns a contiguous run of chains, a multiple of 16 long: phases are read 16 at a time (one 16-byte
-  // load; the phase array is 256-byte aligned and padded, lanes beyond Ccap are masked)
-  const long long per = ((d.Ccap + 1023) / 1024 + 15) / 16 * 16;
-  const long long lo = (long long)tid * per, hi = lo + per < d.Ccap ? lo + per : d.Ccap;
+  // Each WARP owns a contiguous run of chains (a multiple of 32 long) and walks it 32 chains at a time, lane = chain:
+  // one ballot gives the strip's live count and every lane's rank, the loads and the stores are coalesced, the order
+  // stays the chain order.  (One contiguous run per THREAD wrote idx / slot_phase with a 64-byte stride between
+  // lanes: 18 us at 16,384 chains on the one SM this kernel runs on.)
+  const long long per = ((d.Ccap + 31) / 32 + 31) / 32 * 32;
+  const long long lo = (long long)warp * per, hi = lo + per < d.Ccap ? lo + per : d.Ccap;
+  constexpr int U = 8;  // strips in flight
   int cnt = 0;
-  for (long long c = lo; c < hi; c += 16) {
-    const uint4 v = *(const uint4*)(b.phase + c);
-    const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+  for (long long base = lo; base < hi; base += 32 * U) {
+    unsigned char ph[U];
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-      cnt += (c + k < hi) && ((w[k >> 2] >> (8 * (k & 3))) & 0xffu) != LS_PH_DONE;
-  }
-  int inc = cnt;
+    for (int u = 0; u < U; ++u) {
+      const long long c = base + 32 * u + lane;
+      ph[u] = c < hi ? b.phase[c] : (unsigned char)LS_PH_DONE;
+    }
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
+    for (int u = 0; u < U; ++u) cnt += __popc(__ballot_sync(0xffffffffu, ph[u] != LS_PH_DONE));
   }
-  if (lane == 31) wsum[warp] = inc;
+  if (lane == 0) wsum[warp] = cnt;
   __syncthreads();
   if (warp == 0) {
     int w = wsum[lane], wi = w;
@@ -168,18 +168,25 @@ __global__ void __launch_bounds__(1024) ls_compact_kernel(const LsBuf b, const L
     if (lane == 31) total_s = wi;
   }
   __syncthreads();
-  int pos = wsum[warp] + inc - cnt;
-  for (long long c = lo; c < hi; c += 16) {
-    const uint4 v = *(const uint4*)(b.phase + c);
-    const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+  int pos = wsum[warp];
+  const unsigned int lt = (1u << lane) - 1u;
+  for (long long base = lo; base < hi; base += 32 * U) {
+    unsigned char ph[U];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const unsigned char ph = (unsigned char)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
-      if (c + k < hi && ph != LS_PH_DONE) {
-        b.idx[pos] = (int)(c + k);
-        b.slot_phase[pos] = ph;
-        ++pos;
+    for (int u = 0; u < U; ++u) {
+      const long long c = base + 32 * u + lane;
+      ph[u] = c < hi ? b.phase[c] : (unsigned char)LS_PH_DONE;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool live = ph[u] != LS_PH_DONE;
+      const unsigned int m = __ballot_sync(0xffffffffu, live);
+      if (live) {
+        const int o = pos + __popc(m & lt);
+        b.idx[o] = (int)(base + 32 * u + lane);
+        b.slot_phase[o] = ph[u];
       }
+      pos += __popc(m);
     }
   }
   if (tid == 0) {
@@ -352,8 +359,27 @@ __global__ void __launch_bounds__(MAXT, MINB) ls_factor_kernel(const LsBuf b, co
     bj = rem;
   }
   float A[BS][BS];
+  if (d.ksplit > 1) {
+    // split-K parts of the metric GEMM (at most 4): summed in a fixed order by a coalesced pass, in place in part 0
+    // (added inside the block loads below, the strided 32-byte reads of three more parts cost 170 us at c5's shape)
+    float* G0 = b.Gp + (size_t)j * d.PS;
+    const size_t zs = (size_t)d.Ccap * d.PS;
+    for (int m4 = 4 * tid; m4 < d.PS; m4 += 4 * nthr) {
+      float4 v = *(const float4*)(G0 + m4);
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v1 = *(const float4*)(G0 + zs + m4);
+      const float4 v2 = d.ksplit > 2 ? *(const float4*)(G0 + 2 * zs + m4) : z4;
+      const float4 v3 = d.ksplit > 3 ? *(const float4*)(G0 + 3 * zs + m4) : z4;
+      v.x = ((v.x + v1.x) + v2.x) + v3.x;
+      v.y = ((v.y + v1.y) + v2.y) + v3.y;
+      v.z = ((v.z + v1.z) + v2.z) + v3.z;
+      v.w = ((v.w + v1.w) + v2.w) + v3.w;
+      *(float4*)(G0 + m4) = v;
+    }
+    sync();
+  }
   {
-    const float* Gp = b.Gp + (size_t)j * d.P;
+    const float* Gp = b.Gp + (size_t)j * d.PS;
 #pragma unroll
     for (int a_ = 0; a_ < BS; ++a_)
 #pragma unroll
@@ -361,7 +387,10 @@ __global__ void __launch_bounds__(MAXT, MINB) ls_factor_kernel(const LsBuf b, co
         const int i = BS * bi + a_, jj = BS * bj + b_;
         float v = 0.f;
         if (has) {
-          if (i < D && jj <= i) v = Gp[jj * D - jj * (jj - 1) / 2 + (i - jj)];
+          if (i < D && jj <= i) {
+            const int m = jj * D - jj * (jj - 1) / 2 + (i - jj);
+            v = Gp[m];
+          }
           else if (i == jj) v = 1.f;  // identity padding
         }
         A[a_][b_] = v;
@@ -887,6 +916,7 @@ int ls_dims(const gb200_target_desc* t, int64_t C, LsDims* d) {
   }
   d->Ccap = C;
   d->ctiles = (C + FT_N - 1) / FT_N;
+  d->ksplit = ft_pick_ksplit((long long)((d->P + FT_M - 1) / FT_M) * d->ctiles, d->ktF, 148);
   d->alpha = (float)t->params[0];
   return GB200_OK;
 }
@@ -915,7 +945,7 @@ int64_t ls_carve(const LsDims& d, unsigned char* base, LsBuf* b) {
   t.slot_phase = (unsigned char*)take(C);
   t.v = (float*)take(C * D * 4); t.logdet = (float*)take(C * 4);
   t.sbuf = (float*)take((int64_t)d.N * d.ldn * 4);
-  t.Gp = (float*)take(C * (int64_t)d.P * 4); t.Ap = (float*)take(C * (int64_t)d.P * 4);
+  t.Gp = (float*)take(d.ksplit * C * (int64_t)d.PS * 4); t.Ap = (float*)take(C * (int64_t)d.P * 4);
   t.parts = (float*)take((int64_t)d.mtQ * D * C * 4);
   t.lp_parts = (float*)take((int64_t)d.ktF * C * 4);
   t.dHt = (float*)take(D * C * 4); t.lpt = (float*)take(C * 4); t.qT = (float*)take(D * C * 4);
@@ -941,12 +971,12 @@ int ls_launch_eval(const gb200_plan* pl, cudaStream_t s) {
   FtArgs a;
   memset(&a, 0, sizeof(a));
   a.Xtile = b.Xtile; a.N = d.N; a.D = d.D; a.Wt = b.Wt; a.C = d.Ccap; a.n_active = b.n_active; a.alpha = d.alpha;
-  a.out = b.Gp; a.packed = 1;
+  a.out = b.Gp; a.packed = d.PS; a.ksplit = d.ksplit; a.split_stride = d.Ccap * (long long)d.PS;
   int rc = ft_launch_metric_gemm(a, d.ctiles, s);
   if (rc) return rc;
   if (d.BS == 8 && d.fthreads <= 128) ls_factor_kernel<8, false, 128, 4><<<(unsigned)d.Ccap, d.fthreads, ls_factor_smem(d), s>>>(b, d);
   else if (d.BS == 8) ls_factor_kernel<8, false><<<(unsigned)d.Ccap, d.fthreads, ls_factor_smem(d), s>>>(b, d);
-  else if (d.fwarp) ls_factor_kernel<4, true><<<(unsigned)((d.Ccap + 3) / 4), 128, ls_factor_smem(d), s>>>(b, d);
+  else if (d.fwarp) ls_factor_kernel<4, true, 128, 8><<<(unsigned)((d.Ccap + 3) / 4), 128, ls_factor_smem(d), s>>>(b, d);
   else ls_factor_kernel<4, false><<<(unsigned)d.Ccap, d.fthreads, ls_factor_smem(d), s>>>(b, d);
   GB_CHECK_LAUNCH();
   rc = ft_launch_quad_b_packed(b.Ap, d.D, d.Ccap, b.n_active, b.Bt, d.ctiles, s);
@@ -1119,7 +1149,7 @@ int gb200_rmhmc_logreg_plan_create(const gb200_target_desc* t, int64_t C, void* 
   cudaError_t e = cudaSuccess;
   if (d.BS == 8 && d.fthreads <= 128) e = cudaFuncSetAttribute(ls_factor_kernel<8, false, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
   else if (d.BS == 8) e = cudaFuncSetAttribute(ls_factor_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
-  else if (d.fwarp) e = cudaFuncSetAttribute(ls_factor_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
+  else if (d.fwarp) e = cudaFuncSetAttribute(ls_factor_kernel<4, true, 128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
   else e = cudaFuncSetAttribute(ls_factor_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_factor_smem(d));
   if (e != cudaSuccess) { set_error("plan_create: %s", cudaGetErrorString(e)); delete pl; return GB200_ERR_CUDA; }
   rc = ft_set_attributes(d.D);
