@@ -21,6 +21,9 @@ LIB = LIB_DIR / "libgeomb200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC"]
+# experiment builds, e.g. GEOMB200_EXTRA_NVCC_FLAGS=-DGB_FT_TIMING for tools/ft_stamps.py (part of the build digest:
+# unsetting it rebuilds the shipped library)
+FLAGS += os.environ.get("GEOMB200_EXTRA_NVCC_FLAGS", "").split()
 LPC_GROUPS = (1, 2, 4, 8, 32)
 
 

@@ -1,5 +1,8 @@
-"""Experiment tool: per-CTA time stamps of the two tcgen05 GEMMs (library built with -DGB_FT_TIMING).
-usage: ft_stamps.py N D C"""
+"""Experiment tool: per-CTA time stamps of the two tcgen05 GEMMs of one lock-step evaluation.
+Needs a library built with the stamps compiled in:
+    GEOMB200_EXTRA_NVCC_FLAGS=-DGB_FT_TIMING python -m geomjax_b200.build
+    GEOMB200_EXTRA_NVCC_FLAGS=-DGB_FT_TIMING PYTHONPATH=. python tools/ft_stamps.py N D C
+(build again without the variable afterwards: the flag is part of the build digest).  Output: profiles/r02_ft_stamps.txt."""
 import ctypes as Ct
 import sys
 
