@@ -483,11 +483,17 @@ fisher_metric_tc_kernel(const FtArgs a) {
       if (tid == 0) { FT_STAMP(10); }
       // parts[m tile][i][c] = sum_r x[r, i] R[r, c]: a 128 x D x 128 product on the FP32 pipe, register-tiled
       float* pbase = a.parts + (size_t)blockIdx.x * D * a.Ccap;
+      if (D <= 32) {
+        // both halves at once, 4 features x 8 chains per thread (threads 0-127: chains 0-127, 128-255: the rest):
+        // the loop is bound by shared-memory wavefronts, 12 per 32 FMAs this way against 8 per 16 with a 4 x 4 tile
+        const int h = tid >> 7;
+        if (c0 + h * 128 < C) ft_epi_xtr<4, 8>(xs0, DX, St + h * 128, D, pbase, a.Ccap, c0 + h * 128, C, tid & 127);
+      } else {
 #pragma unroll 1
-      for (int h = 0; h < FT_N / 128; ++h) {  // 128 chains at a time
-        if (c0 + h * 128 >= C) break;
-        if (D <= 32) ft_epi_xtr<4, 4>(xs0, DX, St + h * 128, D, pbase, a.Ccap, c0 + h * 128, C, tid);
-        else ft_epi_xtr<8, 8>(xs0, DX, St + h * 128, D, pbase, a.Ccap, c0 + h * 128, C, tid);
+        for (int h = 0; h < FT_N / 128; ++h) {  // 128 chains at a time
+          if (c0 + h * 128 >= C) break;
+          ft_epi_xtr<8, 8>(xs0, DX, St + h * 128, D, pbase, a.Ccap, c0 + h * 128, C, tid);
+        }
       }
     } else if (QUAD) {
       // epilogue: registers -> h[c, n] (chain-major rows of length ldh; lanes = consecutive data rows: coalesced)

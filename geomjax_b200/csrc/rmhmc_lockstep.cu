@@ -228,7 +228,11 @@ __global__ void __launch_bounds__(256) ls_gather_kernel(const LsBuf b, const LsD
 // One block = one (chain tile, K tile); thread = one chain, all 16 data rows of the tile: the X tile [D][16] is staged
 // in shared memory and read as warp-uniform float4 broadcasts, the positions come coalesced from qT -- 5 loads per 16
 // FMAs with no uncoalesced access (the first version, thread = (chain, 4 rows), issued 8 L2-bound loads per 16 FMAs).
-__global__ void __launch_bounds__(FT_N) ls_weights_kernel(const LsBuf b, const LsDims d) {
+// Each thread carries LS_WCPT chains (slots row and row + 128 of the tile): the broadcast X reads, one shared-memory
+// wavefront per 16 FMAs of ONE chain, were what bound this kernel (FMA pipe 39 %); two chains per thread halve them.
+constexpr int LS_WCPT = 2;
+constexpr int LS_WTHREADS = FT_N / LS_WCPT;
+__global__ void __launch_bounds__(LS_WTHREADS) ls_weights_kernel(const LsBuf b, const LsDims d) {
   extern __shared__ __align__(16) float wsm[];  // [D][FT_KT]
   const long long nact = b.n_active[0];
   const int ktiles = d.ktF;
@@ -237,84 +241,105 @@ __global__ void __launch_bounds__(FT_N) ls_weights_kernel(const LsBuf b, const L
   if (ct * FT_N >= nact) return;
   const int kt = (int)(tile - ct * ktiles);
   const int N = d.N, D = d.D, n0 = kt * FT_KT;
-  for (int e = threadIdx.x; e < D * (FT_KT / 4); e += FT_N) {
+  for (int e = threadIdx.x; e < D * (FT_KT / 4); e += LS_WTHREADS) {
     const int i = e / (FT_KT / 4), k4 = e - i * (FT_KT / 4);
     // ldx % 4 == 0 and columns in [N, ldx) are zero; K tiles may reach beyond ldx
     const int n = n0 + 4 * k4;
     *(float4*)(wsm + i * FT_KT + 4 * k4) = n < d.ldx ? __ldg((const float4*)(b.Xt + (size_t)i * d.ldx + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
-  const int row = threadIdx.x;
-  const long long j = ct * FT_N + row;
-  const bool live = j < nact;
-  const bool end = live && b.slot_phase[j] == LS_PH_END;
-  float eta[FT_KT];
+  const long long j0 = ct * FT_N + threadIdx.x;
+  bool live[LS_WCPT], end[LS_WCPT];
 #pragma unroll
-  for (int k = 0; k < FT_KT; ++k) eta[k] = 0.f;
-  if (live) {
-    // positions are fetched CH features ahead (CH independent loads in flight per thread); addresses advance by
+  for (int c = 0; c < LS_WCPT; ++c) {
+    const long long j = j0 + c * LS_WTHREADS;
+    live[c] = j < nact;
+    end[c] = live[c] && b.slot_phase[j] == LS_PH_END;
+  }
+  float eta[LS_WCPT][FT_KT];
+#pragma unroll
+  for (int c = 0; c < LS_WCPT; ++c)
+#pragma unroll
+    for (int k = 0; k < FT_KT; ++k) eta[c][k] = 0.f;
+  if (live[0]) {  // slots are compacted: live[c] implies live[0]
+    // positions are fetched CH features ahead (CH independent loads in flight per chain); addresses advance by
     // pointer bumps and constant offsets (the first version recomputed them per feature: 2.6 instructions per FMA)
     constexpr int CH = 10;
-    const float* tp = b.qT + j;
+    const float* tp = b.qT + j0;
     const float* xp = wsm;
     const size_t cs = (size_t)d.Ccap;
     int i = 0;
     for (; i + CH <= D; i += CH) {
-      float t[CH];
+      float t[LS_WCPT][CH];
 #pragma unroll
-      for (int u = 0; u < CH; ++u) t[u] = __ldg(tp + u * cs);
+      for (int u = 0; u < CH; ++u)
+#pragma unroll
+        for (int c = 0; c < LS_WCPT; ++c) t[c][u] = live[c] ? __ldg(tp + u * cs + c * LS_WTHREADS) : 0.f;
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
 #pragma unroll
         for (int k4 = 0; k4 < FT_KT / 4; ++k4) {
           const float4 x = *(const float4*)(xp + u * FT_KT + 4 * k4);
-          eta[4 * k4 + 0] = fmaf(x.x, t[u], eta[4 * k4 + 0]);
-          eta[4 * k4 + 1] = fmaf(x.y, t[u], eta[4 * k4 + 1]);
-          eta[4 * k4 + 2] = fmaf(x.z, t[u], eta[4 * k4 + 2]);
-          eta[4 * k4 + 3] = fmaf(x.w, t[u], eta[4 * k4 + 3]);
+#pragma unroll
+          for (int c = 0; c < LS_WCPT; ++c) {
+            eta[c][4 * k4 + 0] = fmaf(x.x, t[c][u], eta[c][4 * k4 + 0]);
+            eta[c][4 * k4 + 1] = fmaf(x.y, t[c][u], eta[c][4 * k4 + 1]);
+            eta[c][4 * k4 + 2] = fmaf(x.z, t[c][u], eta[c][4 * k4 + 2]);
+            eta[c][4 * k4 + 3] = fmaf(x.w, t[c][u], eta[c][4 * k4 + 3]);
+          }
         }
       }
       tp += CH * cs;
       xp += CH * FT_KT;
     }
     for (; i < D; ++i) {
-      const float t = __ldg(tp);
+      float t[LS_WCPT];
+#pragma unroll
+      for (int c = 0; c < LS_WCPT; ++c) t[c] = live[c] ? __ldg(tp + c * LS_WTHREADS) : 0.f;
 #pragma unroll
       for (int k4 = 0; k4 < FT_KT / 4; ++k4) {
         const float4 x = *(const float4*)(xp + 4 * k4);
-        eta[4 * k4 + 0] = fmaf(x.x, t, eta[4 * k4 + 0]);
-        eta[4 * k4 + 1] = fmaf(x.y, t, eta[4 * k4 + 1]);
-        eta[4 * k4 + 2] = fmaf(x.z, t, eta[4 * k4 + 2]);
-        eta[4 * k4 + 3] = fmaf(x.w, t, eta[4 * k4 + 3]);
+#pragma unroll
+        for (int c = 0; c < LS_WCPT; ++c) {
+          eta[c][4 * k4 + 0] = fmaf(x.x, t[c], eta[c][4 * k4 + 0]);
+          eta[c][4 * k4 + 1] = fmaf(x.y, t[c], eta[c][4 * k4 + 1]);
+          eta[c][4 * k4 + 2] = fmaf(x.z, t[c], eta[c][4 * k4 + 2]);
+          eta[c][4 * k4 + 3] = fmaf(x.w, t[c], eta[c][4 * k4 + 3]);
+        }
       }
       tp += cs;
       xp += FT_KT;
     }
   }
-  float lp = 0.f;
-  unsigned char* base = b.Wt + (size_t)tile * (2 * FT_B_BYTES) + (size_t)(row >> 3) * FT_SBO + (row & 7) * 16;
 #pragma unroll
-  for (int k4 = 0; k4 < FT_KT / 4; ++k4) {
-    float sg[4], w[4];
+  for (int c = 0; c < LS_WCPT; ++c) {
+    const int row = threadIdx.x + c * LS_WTHREADS;
+    const long long j = j0 + c * LS_WTHREADS;
+    float lp = 0.f;
+    unsigned char* base = b.Wt + (size_t)tile * (2 * FT_B_BYTES) + (size_t)(row >> 3) * FT_SBO + (row & 7) * 16;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int n = n0 + 4 * k4 + e;
-      const float et = eta[4 * k4 + e];
-      sg[e] = 1.f / (1.f + expf(-et));
-      w[e] = (live && n < N) ? sg[e] * (1.f - sg[e]) : 0.f;
-      if (end && n < N) lp += __ldg(b.y + n) * et - (fmaxf(et, 0.f) + log1pf(expf(-fabsf(et))));  // jnp.logaddexp(0, eta)
+    for (int k4 = 0; k4 < FT_KT / 4; ++k4) {
+      float sg[4], w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = n0 + 4 * k4 + e;
+        const float et = eta[c][4 * k4 + e];
+        sg[e] = 1.f / (1.f + expf(-et));
+        w[e] = (live[c] && n < N) ? sg[e] * (1.f - sg[e]) : 0.f;
+        if (end[c] && n < N) lp += __ldg(b.y + n) * et - (fmaxf(et, 0.f) + log1pf(expf(-fabsf(et))));  // jnp.logaddexp(0, eta)
+      }
+      if (live[c]) {  // sT[data row][chain slot]: lanes = consecutive slots
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n0 + 4 * k4 + e < N) b.sbuf[(size_t)(n0 + 4 * k4 + e) * d.ldn + j] = sg[e];
+      }
+      float4 hi, lo;
+      ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
+      *(float4*)(base + k4 * FT_LBO) = hi;
+      *(float4*)(base + k4 * FT_LBO + FT_B_BYTES) = lo;
     }
-    if (live) {  // sT[data row][chain slot]: lanes = consecutive slots
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (n0 + 4 * k4 + e < N) b.sbuf[(size_t)(n0 + 4 * k4 + e) * d.ldn + j] = sg[e];
-    }
-    float4 hi, lo;
-    ft_split(w[0], hi.x, lo.x); ft_split(w[1], hi.y, lo.y); ft_split(w[2], hi.z, lo.z); ft_split(w[3], hi.w, lo.w);
-    *(float4*)(base + k4 * FT_LBO) = hi;
-    *(float4*)(base + k4 * FT_LBO + FT_B_BYTES) = lo;
+    if (end[c]) b.lp_parts[(size_t)kt * d.Ccap + j] = lp;
   }
-  if (end) b.lp_parts[(size_t)kt * d.Ccap + j] = lp;
 }
 
 // ---- per-chain dense algebra: blocked Cholesky / inverse with the matrix in REGISTERS ---------------------------
@@ -965,7 +990,7 @@ int ls_launch_eval(const gb200_plan* pl, cudaStream_t s) {
     dim3 gg((unsigned)((d.Ccap + 31) / 32), (unsigned)((d.D + 31) / 32));
     ls_gather_kernel<<<gg, 256, 0, s>>>(b, d);
     GB_CHECK_LAUNCH();
-    ls_weights_kernel<<<(unsigned)(d.ctiles * d.ktF), FT_N, sizeof(float) * d.D * FT_KT, s>>>(b, d);
+    ls_weights_kernel<<<(unsigned)(d.ctiles * d.ktF), LS_WTHREADS, sizeof(float) * d.D * FT_KT, s>>>(b, d);
     GB_CHECK_LAUNCH();
   }
   FtArgs a;
