@@ -174,3 +174,24 @@ def test_chees_host_recurrences_match_oracle():
         da = chees._da_update(da, gr)
         oda = OA.da_update(oda, np.float64(gr))
         assert abs(da[0] - float(oda["log_x"])) < 1e-12 and abs(da[1] - float(oda["log_x_avg"])) < 1e-12
+
+
+def test_lockstep_plan_workspace_is_host_arithmetic():
+    """gb200_rmhmc_logreg_plan_workspace only sizes the carve (no device call): positive, growing with the chain
+    count, ~28 GB for c5 as named (131,072 chains, N = 10,000, D = 100), and refused for shapes the plan does not take."""
+    import ctypes as Ct
+    from geomjax_b200 import _native as N
+
+    def ws(Nrows, D, chains, ldx=None):
+        t = N.TargetDesc()
+        t.kind, t.metric, t.D, t.N = N.TARGET_LOGREG, N.METRIC_TARGET, D, Nrows
+        t.params[0], t.params[1] = 0.01, float(ldx if ldx is not None else (Nrows + 3) // 4 * 4)
+        t.y = t.vec0 = Ct.c_void_p(256)  # never dereferenced by the size computation
+        return int(N.lib().gb200_rmhmc_logreg_plan_workspace(Ct.byref(t), chains))
+
+    sizes = [ws(1000, 25, c) for c in (1, 3, 256, 257, 2048, 16384)]
+    assert all(s > 0 for s in sizes) and sizes == sorted(sizes)
+    assert 20e9 < ws(10000, 100, 131072) < 40e9
+    assert ws(1000, 125, 64) < 0        # D > 124
+    assert ws(1000, 25, 0) < 0          # no chains
+    assert ws(1000, 25, 64, ldx=1001) < 0  # ldx must be a multiple of 4
